@@ -1,0 +1,719 @@
+/* lzb_containers.cu -- host front ends that turn container byte streams into units for the GPU:
+ *
+ *   LZMA2 : walk the chunk headers (reference Lzma2Dec.c:14-26,98-157) and cut at dictionary resets
+ *           (control 0x01 or >= 0xE0) -- the only points where a chunk depends on nothing before it
+ *           (SURVEY.md F2).  The decoding warp re-reads the headers of its own unit.
+ *   xz    : forward walk of stream header / block headers / LZMA2 chunk headers / index / footer
+ *           (reference XzDec.c:482-556,604-870, Xz.c:12-43); the reference's block headers carry no
+ *           sizes (F10), the chunk walk is what finds a block's end.  Also the backward index reader
+ *           (reference XzIn.c:71-114,141-224).
+ *
+ * Results of the per-unit decodes are stitched back in stream order so that the whole-buffer calls
+ * return what the reference's sequential decoder returns: the first failing unit decides.
+ */
+#include "lzb_host.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+enum { LZB_FINISH_UNIT = 2 };   /* internal: validate the unit's last chunk, then stop at its end */
+
+/* ------------------------------------------------------------------ LZMA2 walk ---------------- */
+struct L2Walk
+{
+  std::vector<LzbUnit> units;   /* offsets relative to the walked buffer, dst_off cumulative */
+  size_t end_off = 0;           /* just past the 0x00 marker, or where the walk stopped */
+  bool has_eos = false;
+  bool malformed = false;       /* stopped at a header the decoder will reject */
+  bool truncated = false;       /* stopped because a header or payload runs past the end */
+  uint64_t unpack_total = 0;
+};
+
+static SRes lzma2_dict_size(Byte prop, UInt32 *dict)
+{
+  if (prop > 40) return SZ_ERROR_UNSUPPORTED;                      /* Lzma2Dec.c:64-66 */
+  *dict = prop == 40 ? 0xFFFFFFFFu : ((UInt32)(2 | (prop & 1)) << (prop / 2 + 11));
+  return SZ_OK;
+}
+
+static void lzma2_walk(const Byte *src, size_t n, UInt32 dict, L2Walk &w)
+{
+  size_t p = 0;
+  uint64_t out = 0;
+  while (p < n)
+  {
+    const Byte c = src[p];
+    size_t hdr, pack, unpack;
+    unsigned lclp = 0, pb = 0;
+    bool has_props = false;
+    if (c == 0) { p++; w.has_eos = true; break; }
+    if ((c & 0x80) == 0)
+    {
+      if (c > 2) { w.malformed = true; break; }
+      hdr = 3;
+      if (n - p < hdr) { w.truncated = true; break; }
+      unpack = (((size_t)src[p + 1] << 8) | src[p + 2]) + 1;
+      pack = unpack;
+    }
+    else
+    {
+      hdr = 5 + (((c >> 5) & 3) >= 2 ? 1 : 0);
+      if (n - p < hdr) { w.truncated = true; break; }
+      unpack = (((size_t)(c & 0x1F) << 16) | ((size_t)src[p + 1] << 8) | src[p + 2]) + 1;
+      pack = (((size_t)src[p + 3] << 8) | src[p + 4]) + 1;
+      if (hdr == 6)
+      {
+        unsigned b = src[p + 5];
+        if (b >= 225 || (b % 9) + ((b / 9) % 5) > 4) { w.malformed = true; break; }
+        lclp = (b % 9) + ((b / 9) % 5);
+        pb = b / 45;
+        has_props = true;
+      }
+    }
+    if (c == 1 || c >= 0xE0 || w.units.empty())
+    {
+      LzbUnit u;
+      memset(&u, 0, sizeof u);
+      u.src_off = p; u.dst_off = out; u.dict_size = dict;
+      u.codec = LZB_CODEC_LZMA2; u.finish = LZB_FINISH_UNIT;
+      w.units.push_back(u);
+    }
+    LzbUnit &u = w.units.back();
+    if (has_props) { if (lclp > u.lc) u.lc = (uint8_t)lclp; if (pb > u.pb) u.pb = (uint8_t)pb; }
+    if (n - p - hdr < pack) { w.truncated = true; u.src_len = (uint32_t)std::min<size_t>(n - u.src_off, 0xFFFFFFFFu); break; }
+    if ((uint64_t)u.dst_cap + unpack > 0xFFFFFFFFull || (p + hdr + pack - u.src_off) > 0xFFFFFFFFull) { w.malformed = true; break; }
+    u.dst_cap += (uint32_t)unpack;
+    u.src_len = (uint32_t)(p + hdr + pack - u.src_off);
+    out += unpack;
+    p += hdr + pack;
+  }
+  w.end_off = p;
+  w.unpack_total = out;
+}
+
+extern "C" SRes Lzma2_IndexUnits(const Byte *src, size_t srcLen, Byte prop, LzbUnit *units, size_t maxUnits, size_t *n,
+                                 size_t *endOffset, int *hasEos)
+{
+  UInt32 dict;
+  SRes r = lzma2_dict_size(prop, &dict);
+  if (r != SZ_OK) return r;
+  L2Walk w;
+  lzma2_walk(src, srcLen, dict, w);
+  *n = w.units.size();
+  for (size_t i = 0; i < w.units.size() && i < maxUnits; i++) units[i] = w.units[i];
+  *endOffset = w.end_off;
+  *hasEos = w.has_eos ? 1 : 0;
+  return w.malformed ? SZ_ERROR_DATA : SZ_OK;
+}
+
+/* Shape the walked units for one whole-buffer call with output limit `cap` and the caller's finish
+ * mode: units past the limit are dropped; the last decoded unit sees the rest of the input and of the
+ * output so that it behaves exactly like the sequential decoder from there on. */
+static void shape_units(L2Walk &w, size_t in_size, size_t cap, int finish, bool dirty_tail)
+{
+  if (w.units.empty())
+  {
+    LzbUnit u;
+    memset(&u, 0, sizeof u);
+    u.codec = LZB_CODEC_LZMA2;
+    w.units.push_back(u);
+  }
+  size_t keep = 0;
+  uint64_t acc = 0;
+  for (; keep < w.units.size(); keep++)
+  {
+    if (keep + 1 == w.units.size()) { keep++; break; }
+    if (acc + w.units[keep].dst_cap >= cap) { keep++; break; }        /* limit falls inside or at the end of this unit */
+    acc += w.units[keep].dst_cap;
+  }
+  w.units.resize(keep);
+  LzbUnit &last = w.units.back();
+  last.src_len = (uint32_t)std::min<size_t>(in_size - last.src_off, 0xFFFFFFFFu);
+  last.dst_cap = (uint32_t)std::min<uint64_t>(cap - std::min<uint64_t>(cap, last.dst_off), 0xFFFFFFFFu);
+  last.finish = (uint8_t)finish;
+  if (dirty_tail) { last.lc = 4; last.lp = 0; last.pb = 4; }        /* headers the walk did not vet: worst-case model */
+}
+
+extern "C" SRes Lzma2DecodeParallel(LzbContext *c, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen, Byte prop,
+                                    ELzmaFinishMode finishMode, ELzmaStatus *status)
+{
+  const size_t cap = *destLen, in_size = *srcLen;
+  *destLen = *srcLen = 0;
+  *status = LZMA_STATUS_NOT_SPECIFIED;
+  UInt32 dict;
+  SRes r = lzma2_dict_size(prop, &dict);
+  if (r != SZ_OK) return r;
+  if (!c) c = lzb_default_context();
+  if (!c) return SZ_ERROR_FAIL;
+  L2Walk w;
+  lzma2_walk(src, in_size, dict, w);
+  /* a unit that would start exactly at the limit is never reached with FINISH_ANY */
+  shape_units(w, in_size, cap, (int)finishMode, w.malformed || w.truncated || !w.has_eos);
+  for (auto &u : w.units) u.dict_size = dict;
+  std::vector<LzbResult> res(w.units.size());
+  r = Lzb_DecodeUnitsHost(c, src, in_size, dest, cap, w.units.data(), res.data(), w.units.size());
+  if (r != SZ_OK) return r;
+  size_t done = 0;
+  for (size_t k = 0; k < w.units.size(); k++)
+  {
+    const LzbUnit &u = w.units[k];
+    const LzbResult &x = res[k];
+    done += x.dst_done;
+    const bool last = k + 1 == w.units.size();
+    const bool clean = x.res == SZ_OK && x.status == LZMA_STATUS_NOT_FINISHED && x.dst_done == u.dst_cap;
+    if (last || !clean)
+    {
+      *destLen = done;
+      *srcLen = (size_t)u.src_off + x.src_used;
+      *status = (ELzmaStatus)x.status;
+      return x.res;
+    }
+  }
+  return SZ_ERROR_FAIL;
+}
+
+extern "C" SRes Lzma2Decode(Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen, Byte prop,
+                            ELzmaFinishMode finishMode, ELzmaStatus *status, ISzAlloc *alloc)
+{
+  (void)alloc;
+  SRes r = Lzma2DecodeParallel(nullptr, dest, destLen, src, srcLen, prop, finishMode, status);
+  if (r == SZ_OK && *status == LZMA_STATUS_NEEDS_MORE_INPUT) r = SZ_ERROR_INPUT_EOF;   /* Lzma2Dec.c:351-352 */
+  return r;
+}
+
+/* ------------------------------------------------------------------ xz helpers ---------------- */
+static const Byte k_xz_magic[6] = { 0xFD, '7', 'z', 'X', 'Z', 0 };
+
+/* host CRC-32 of a few header bytes (container framing only; payload digests run on the GPU) */
+static uint32_t small_crc32(const Byte *p, size_t n)
+{
+  uint32_t v = 0xFFFFFFFFu;
+  for (size_t i = 0; i < n; i++)
+  {
+    v ^= p[i];
+    for (int k = 0; k < 8; k++) v = (v >> 1) ^ (0xEDB88320u & (0u - (v & 1)));
+  }
+  return ~v;
+}
+
+extern "C" unsigned Xz_ReadVarInt(const Byte *p, size_t maxSize, UInt64 *value)
+{
+  /* reference XzDec.c:30-44 */
+  unsigned lim = maxSize > 9 ? 9 : (unsigned)maxSize;
+  *value = 0;
+  for (unsigned i = 0; i < lim;)
+  {
+    Byte b = p[i];
+    *value |= (UInt64)(b & 0x7F) << (7 * i++);
+    if ((b & 0x80) == 0) return (b == 0 && i != 1) ? 0 : i;
+  }
+  return 0;
+}
+
+static unsigned write_varint(Byte *buf, UInt64 v)
+{
+  unsigned i = 0;
+  do { buf[i++] = (Byte)((v & 0x7F) | 0x80); v >>= 7; } while (v != 0);
+  buf[i - 1] &= 0x7F;
+  return i;
+}
+
+extern "C" unsigned XzFlags_GetCheckSize(CXzStreamFlags f)
+{
+  int t = f & 0xF;                                                 /* reference Xz.c:39-43 */
+  return t == 0 ? 0 : (4u << ((t - 1) / 3));
+}
+
+extern "C" SRes Xz_ParseHeader(CXzStreamFlags *p, const Byte *buf)
+{
+  /* reference XzDec.c:482-489 */
+  *p = (CXzStreamFlags)(((unsigned)buf[6] << 8) | buf[7]);
+  if (small_crc32(buf + 6, 2) != lzb_le32(buf + 8)) return SZ_ERROR_NO_ARCHIVE;
+  return *p <= 0xF ? SZ_OK : SZ_ERROR_UNSUPPORTED;
+}
+
+struct XzFilterSpec { UInt64 id; UInt32 props_size; Byte props[20]; };
+
+/* reference XzDec.c:505-556 */
+static SRes parse_block_header(const Byte *h, XzFilterSpec *f, int *nf)
+{
+  const UInt32 hs = (UInt32)h[0] << 2;
+  unsigned pos = 1;
+  UInt64 v;
+  if (small_crc32(h, hs) != lzb_le32(h + hs)) return SZ_ERROR_ARCHIVE;
+  if (pos == hs) return SZ_ERROR_ARCHIVE;
+  const unsigned flags = h[pos++];
+  if (flags & 0x40)
+  {
+    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &v);
+    if (!s) return SZ_ERROR_ARCHIVE;
+    pos += s;
+    if (v == 0 || v + hs >= (UInt64)1 << 63) return SZ_ERROR_ARCHIVE;
+  }
+  if (flags & 0x80)
+  {
+    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &v);
+    if (!s) return SZ_ERROR_ARCHIVE;
+    pos += s;
+  }
+  *nf = (int)(flags & 3) + 1;
+  for (int i = 0; i < *nf; i++)
+  {
+    UInt64 sz;
+    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &f[i].id);
+    if (!s) return SZ_ERROR_ARCHIVE;
+    pos += s;
+    s = Xz_ReadVarInt(h + pos, hs - pos, &sz);
+    if (!s) return SZ_ERROR_ARCHIVE;
+    pos += s;
+    if (sz > hs - pos || sz > 20) return SZ_ERROR_ARCHIVE;
+    f[i].props_size = (UInt32)sz;
+    memcpy(f[i].props, h + pos, (size_t)sz);
+    pos += (unsigned)sz;
+  }
+  while (pos < hs) if (h[pos++] != 0) return SZ_ERROR_ARCHIVE;
+  return SZ_OK;
+}
+
+/* Filter chains on the hot path: [x86 | delta] + LZMA2 (reference XzDec.c:63-106,356-371,558-588).
+ * The other branch converters / longer chains are legal in the reference and out of scope here. */
+static SRes classify_chain(const XzFilterSpec *f, int nf, LzbXzBlock *b)
+{
+  const XzFilterSpec &last = f[nf - 1];
+  b->filter = LZB_FILTER_NONE; b->filter_param = 0;
+  if (last.id != 0x21 || last.props_size != 1 || last.props[0] > 40) return SZ_ERROR_UNSUPPORTED;
+  b->lzma2_prop = last.props[0];
+  if (nf == 1) return SZ_OK;
+  if (nf > 2) { lzb_set_error("xz filter chains longer than 2 are outside the GPU hot path"); return SZ_ERROR_UNSUPPORTED; }
+  if (f[0].id == 3)
+  {
+    if (f[0].props_size != 1) return SZ_ERROR_UNSUPPORTED;
+    b->filter = LZB_FILTER_DELTA; b->filter_param = (UInt32)f[0].props[0] + 1;
+    return SZ_OK;
+  }
+  if (f[0].id == 4)
+  {
+    if (f[0].props_size == 4) b->filter_param = lzb_le32(f[0].props);
+    else if (f[0].props_size != 0) return SZ_ERROR_UNSUPPORTED;
+    b->filter = LZB_FILTER_X86;
+    return SZ_OK;
+  }
+  lzb_set_error("xz filter id %llu is outside the GPU hot path", (unsigned long long)f[0].id);
+  return SZ_ERROR_UNSUPPORTED;
+}
+
+/* ------------------------------------------------------------------ xz forward walk ----------- */
+struct XzWalk
+{
+  std::vector<LzbXzBlock> blocks;
+  std::vector<LzbUnit> units;          /* src_off absolute in the file, dst_off absolute in the output */
+  std::vector<SRes> after_block;       /* structural error met right after block k's payload (padding) */
+  SRes end_res = SZ_OK;                /* verdict if every walked block decodes and verifies */
+  int end_status = CODER_STATUS_NEEDS_MORE_INPUT;
+  size_t end_src = 0;
+  bool finished = false;
+  uint64_t out_total = 0;
+  int partial = -1;                    /* index of a block whose payload is cut short / malformed */
+};
+
+static void xz_walk(const Byte *src, size_t n, XzWalk &w)
+{
+  size_t ip = 0;
+  uint64_t op = 0;
+#define XZ_END(code, st, at) do { w.end_res = (code); w.end_status = (st); w.end_src = (at); return; } while (0)
+#define XZ_STARVED() XZ_END(SZ_OK, CODER_STATUS_NEEDS_MORE_INPUT, n)
+  for (;;)
+  {
+    for (size_t k = 0; k < 6; k++)
+    {
+      if (ip + k >= n) XZ_STARVED();
+      if (src[ip + k] != k_xz_magic[k]) XZ_END(SZ_ERROR_NO_ARCHIVE, CODER_STATUS_NOT_SPECIFIED, ip + k);
+    }
+    if (n - ip <= 12) XZ_STARVED();                  /* the header is parsed when the next byte arrives */
+    CXzStreamFlags flags;
+    SRes r = Xz_ParseHeader(&flags, src + ip);
+    ip += 12;
+    if (r != SZ_OK) XZ_END(r, CODER_STATUS_NOT_SPECIFIED, ip);
+    const unsigned ctype = flags & 0xF, csz = XzFlags_GetCheckSize(flags);
+    const size_t first_block = w.blocks.size();
+
+    for (;;)
+    {
+      if (ip >= n) XZ_STARVED();
+      if (src[ip] == 0) break;
+      const UInt32 hs = ((UInt32)src[ip] << 2) + 4;
+      if (n - ip <= hs) XZ_STARVED();
+      XzFilterSpec fs[4];
+      int nf = 0;
+      LzbXzBlock b;
+      memset(&b, 0, sizeof b);
+      r = parse_block_header(src + ip, fs, &nf);
+      b.hdr_off = ip; b.hdr_size = hs;
+      ip += hs;
+      if (r != SZ_OK) XZ_END(r, CODER_STATUS_NOT_SPECIFIED, ip);
+      r = classify_chain(fs, nf, &b);
+      if (r != SZ_OK) XZ_END(r, CODER_STATUS_NOT_SPECIFIED, ip);
+      if (ctype == 10) { lzb_set_error("xz SHA-256 block check is outside the GPU hot path"); XZ_END(SZ_ERROR_UNSUPPORTED, CODER_STATUS_NOT_SPECIFIED, ip); }
+      b.check_type = (uint8_t)ctype;
+      UInt32 dict;
+      lzma2_dict_size(b.lzma2_prop, &dict);
+      L2Walk lw;
+      lzma2_walk(src + ip, n - ip, dict, lw);
+      b.data_off = ip;
+      b.first_unit = (uint32_t)w.units.size();
+      const bool whole = lw.has_eos;
+      if (!whole)
+      {
+        /* payload cut short or malformed: hand everything that is left to the decoder, it returns what
+         * the sequential decoder returns from here (NEEDS_MORE_INPUT or SZ_ERROR_DATA) */
+        shape_units(lw, n - ip, (size_t)0xFFFFFFFFu, LZMA_FINISH_ANY, true);
+      }
+      for (auto u : lw.units)
+      {
+        u.src_off += ip;
+        u.dst_off += op;
+        w.units.push_back(u);
+      }
+      if (whole && !lw.units.empty())
+      {
+        /* the 0x00 end marker belongs to the last unit: with FINISH_END it must be there */
+        LzbUnit &last = w.units.back();
+        last.src_len = (uint32_t)(ip + lw.end_off - last.src_off);
+        last.finish = LZMA_FINISH_END;
+      }
+      if (whole && lw.units.empty())
+      {
+        LzbUnit u;                                   /* empty block: a lone end marker */
+        memset(&u, 0, sizeof u);
+        u.src_off = ip; u.src_len = 1; u.dst_off = op; u.dst_cap = 0; u.dict_size = dict;
+        u.codec = LZB_CODEC_LZMA2; u.finish = LZMA_FINISH_END;
+        w.units.push_back(u);
+      }
+      b.n_units = (uint32_t)w.units.size() - b.first_unit;
+      b.pack_size = lw.end_off;
+      b.unpack_size = lw.unpack_total;
+      b.complete = whole ? 1 : 0;
+      w.blocks.push_back(b);
+      w.after_block.push_back(SZ_OK);
+      if (!whole) { w.partial = (int)w.blocks.size() - 1; XZ_END(SZ_OK, CODER_STATUS_NEEDS_MORE_INPUT, n); }
+      ip += lw.end_off;
+      op += lw.unpack_total;
+      LzbXzBlock &bb = w.blocks.back();
+      /* padding to a multiple of four, then the stored digest (reference XzDec.c:728-760) */
+      const size_t pad = (4 - (lw.end_off & 3)) & 3;
+      for (size_t k = 0; k < pad; k++)
+      {
+        if (ip >= n) XZ_STARVED();
+        if (src[ip++] != 0) { w.after_block.back() = SZ_ERROR_CRC; XZ_END(SZ_ERROR_CRC, CODER_STATUS_NOT_SPECIFIED, ip); }
+      }
+      if (n - ip < csz || (csz != 0 && n - ip == csz)) { bb.complete = 2; XZ_STARVED(); }   /* digest not all here */
+      bb.check_off = ip;
+      bb.expect = csz == 4 ? lzb_le32(src + ip) : (csz == 8 ? lzb_le64(src + ip) : 0);
+      ip += csz;
+      w.out_total = op;
+    }
+
+    /* index + footer (reference XzDec.c:694-703,762-842) */
+    {
+      const uint64_t nblk = w.blocks.size() - first_block;
+      Byte pre[16];
+      const size_t pre_len = 1 + write_varint(pre + 1, nblk), idx_start = ip;
+      pre[0] = 0;
+      for (size_t k = 0; k < pre_len; k++)
+      {
+        if (ip >= n) XZ_STARVED();
+        if (src[ip++] != pre[k]) XZ_END(SZ_ERROR_CRC, CODER_STATUS_NOT_SPECIFIED, ip);
+      }
+      std::vector<Byte> rec;
+      for (size_t k = first_block; k < w.blocks.size(); k++)
+      {
+        Byte t[24];
+        unsigned m = write_varint(t, w.blocks[k].pack_size + w.blocks[k].hdr_size + csz);
+        m += write_varint(t + m, w.blocks[k].unpack_size);
+        rec.insert(rec.end(), t, t + m);
+      }
+      if (n - ip < rec.size()) XZ_STARVED();
+      const size_t rec_at = ip;
+      ip += rec.size();
+      while (((ip - idx_start) & 3) != 0)
+      {
+        if (ip >= n) XZ_STARVED();
+        if (src[ip++] != 0) XZ_END(SZ_ERROR_CRC, CODER_STATUS_NOT_SPECIFIED, ip);
+      }
+      if (ip >= n) XZ_STARVED();
+      if (!rec.empty() && memcmp(src + rec_at, rec.data(), rec.size()) != 0) XZ_END(SZ_ERROR_CRC, CODER_STATUS_NOT_SPECIFIED, ip);
+      const size_t idx_len = ip - idx_start;
+      if (n - ip < 4) XZ_STARVED();
+      const uint32_t crc = small_crc32(src + idx_start, idx_len);
+      ip += 4;
+      if (ip >= n) XZ_STARVED();
+      if (crc != lzb_le32(src + ip - 4)) XZ_END(SZ_ERROR_CRC, CODER_STATUS_NOT_SPECIFIED, ip);
+      if (n - ip < 12) XZ_STARVED();
+      const Byte *f = src + ip;
+      const bool ok = (idx_len + 4 == (((size_t)lzb_le32(f + 4) + 1) << 2)) && lzb_le32(f) == small_crc32(f + 4, 6) &&
+                      flags == (((unsigned)f[8] << 8) | f[9]) && f[10] == 'Y' && f[11] == 'Z';
+      ip += 12;
+      if (!ok) XZ_END(SZ_ERROR_CRC, CODER_STATUS_NOT_SPECIFIED, ip);
+    }
+    {
+      size_t padn = 0;
+      while (ip < n && src[ip] == 0) { ip++; padn++; }
+      if (ip >= n) { w.finished = (padn & 3) == 0; XZ_END(SZ_OK, CODER_STATUS_NEEDS_MORE_INPUT, ip); }
+      if ((padn & 3) != 0) XZ_END(SZ_ERROR_NO_ARCHIVE, CODER_STATUS_NOT_SPECIFIED, ip);
+    }
+  }
+#undef XZ_END
+#undef XZ_STARVED
+}
+
+extern "C" SRes XzDecodeParallel(LzbContext *c, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
+                                 ECoderStatus *status, UInt64 *numBlocks, int *streamFinished)
+{
+  const size_t cap = *destLen, in_size = *srcLen;
+  *destLen = *srcLen = 0;
+  *status = CODER_STATUS_NOT_SPECIFIED; *numBlocks = 0; *streamFinished = 0;
+  if (!c) c = lzb_default_context();
+  if (!c) return SZ_ERROR_FAIL;
+  XzWalk w;
+  xz_walk(src, in_size, w);
+  if (w.units.empty())
+  {
+    *srcLen = w.end_src; *status = (ECoderStatus)w.end_status; *streamFinished = w.finished;
+    return w.end_res;
+  }
+  /* room: every walked block must fit (round-1 limit, include/lzb200.h) */
+  uint64_t need = 0;
+  for (auto &u : w.units) need = std::max<uint64_t>(need, u.dst_off + (u.dst_cap == 0xFFFFFFFFu ? 0 : u.dst_cap));
+  if (need > cap) { lzb_set_error("XzDecodeParallel: output buffer smaller than the walked blocks (%llu > %zu)", (unsigned long long)need, cap); return SZ_ERROR_UNSUPPORTED; }
+  for (auto &u : w.units) if ((uint64_t)u.dst_off + u.dst_cap > cap) u.dst_cap = (uint32_t)(cap - u.dst_off);
+
+  /* single-unit blocks: filter + digest fused into the decode launch; others: second pass */
+  std::vector<LzbUnit> post;
+  std::vector<size_t> post_block;
+  for (size_t k = 0; k < w.blocks.size(); k++)
+  {
+    LzbXzBlock &b = w.blocks[k];
+    if (b.complete != 1) continue;
+    const bool has_check = b.check_type == LZB_CHECK_CRC32 || b.check_type == LZB_CHECK_CRC64;
+    if (b.filter == LZB_FILTER_NONE && !has_check) continue;
+    if (b.n_units == 1)
+    {
+      LzbUnit &u = w.units[b.first_unit];
+      u.filter = (uint8_t)b.filter; u.filter_param = b.filter_param;
+      if (has_check) { u.check = b.check_type; u.flags |= LZB_UNIT_VERIFY; u.expect = b.expect; }
+    }
+    else
+    {
+      LzbUnit u;
+      memset(&u, 0, sizeof u);
+      u.dst_off = w.units[b.first_unit].dst_off; u.dst_cap = (uint32_t)b.unpack_size;
+      u.filter = (uint8_t)b.filter; u.filter_param = b.filter_param;
+      if (has_check) { u.check = b.check_type; u.flags |= LZB_UNIT_VERIFY; u.expect = b.expect; }
+      post.push_back(u); post_block.push_back(k);
+    }
+  }
+  std::vector<LzbResult> res(w.units.size());
+  SRes r = Lzb_DecodeUnitsHost(c, src, in_size, dest, cap, w.units.data(), res.data(), w.units.size());
+  if (r != SZ_OK) return r;
+
+  /* stitch in stream order: the first failing unit / digest / padding decides */
+  uint64_t done = 0;
+  std::vector<SRes> block_res(w.blocks.size(), SZ_OK);
+  for (size_t k = 0; k < w.blocks.size(); k++)
+  {
+    const LzbXzBlock &b = w.blocks[k];
+    for (uint32_t j = 0; j < b.n_units; j++)
+    {
+      const LzbUnit &u = w.units[b.first_unit + j];
+      const LzbResult &x = res[b.first_unit + j];
+      const bool lastu = j + 1 == b.n_units;
+      done += x.dst_done;
+      bool clean;
+      if (b.complete && lastu) clean = x.res == SZ_OK && x.status == LZMA_STATUS_FINISHED_WITH_MARK;
+      else if (!lastu) clean = x.res == SZ_OK && x.status == LZMA_STATUS_NOT_FINISHED && x.dst_done == u.dst_cap;
+      else clean = false;                                /* cut-short block: its last unit ends the call */
+      if (!clean)
+      {
+        *destLen = (size_t)done; *numBlocks = k;
+        if (x.res != SZ_OK) { *srcLen = (size_t)u.src_off + x.src_used; return x.res; }
+        *srcLen = in_size; *status = CODER_STATUS_NEEDS_MORE_INPUT;
+        return SZ_OK;
+      }
+    }
+  }
+  if (!post.empty())
+  {
+    /* multi-unit blocks: BCJ/Delta + digest over the whole block, now that all of it is decoded */
+    std::vector<LzbResult> pres(post.size());
+    std::lock_guard<std::mutex> g(c->mu);
+    LzbSlot &s = c->slot[0];
+    uint64_t lo = ~0ull, hi = 0;
+    for (auto &u : post) { lo = std::min<uint64_t>(lo, u.dst_off); hi = std::max<uint64_t>(hi, u.dst_off + u.dst_cap); }
+    if (!lzb_slot_reserve(c, s, 0, (size_t)(hi - lo), post.size(), 0)) return SZ_ERROR_MEM;
+    std::vector<LzbUnit> rel = post;
+    for (auto &u : rel) u.dst_off -= lo;
+    bool ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_out, dest + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s.stream), "H2D blocks") &&
+              lzb_cuda_ok(cudaMemcpyAsync(s.d_units, rel.data(), rel.size() * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D units");
+    if (!ok) return SZ_ERROR_FAIL;
+    int rc = lzb_launch_post_only(s.d_out, s.d_units, s.d_results, (uint32_t)rel.size(), s.stream);
+    if (rc != 0) { lzb_set_error("post launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+    for (auto &u : post)
+      ok = ok && lzb_cuda_ok(cudaMemcpyAsync(dest + u.dst_off, s.d_out + (u.dst_off - lo), u.dst_cap, cudaMemcpyDeviceToHost, s.stream), "D2H blocks");
+    ok = ok && lzb_cuda_ok(cudaMemcpyAsync(pres.data(), s.d_results, pres.size() * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results") &&
+         lzb_cuda_ok(cudaStreamSynchronize(s.stream), "post kernel");
+    if (!ok) return SZ_ERROR_FAIL;
+    for (size_t i = 0; i < post.size(); i++) block_res[post_block[i]] = pres[i].res;
+  }
+  done = 0;
+  for (size_t k = 0; k < w.blocks.size(); k++)
+  {
+    const LzbXzBlock &b = w.blocks[k];
+    if (b.complete == 0) break;
+    done += b.unpack_size;
+    SRes br = block_res[k];
+    if (b.n_units == 1 && res[b.first_unit].res != SZ_OK) br = res[b.first_unit].res;
+    if (w.after_block[k] != SZ_OK || (br != SZ_OK && b.complete == 1))
+    {
+      *destLen = (size_t)done; *numBlocks = k + 1;
+      *srcLen = (size_t)(b.complete == 1 ? b.check_off + XzFlags_GetCheckSize(b.check_type) : b.data_off + b.pack_size);
+      return w.after_block[k] != SZ_OK ? w.after_block[k] : br;
+    }
+    *numBlocks = k + 1;
+  }
+  *destLen = (size_t)done;
+  *srcLen = w.end_src;
+  *status = (ECoderStatus)w.end_status;
+  *streamFinished = w.finished ? 1 : 0;
+  return w.end_res;
+}
+
+/* ------------------------------------------------------------------ xz backward index --------- */
+extern "C" SRes Xz_ReadIndexBackward(const Byte *src, size_t srcLen, LzbXzBlock *blocks, size_t maxBlocks, size_t *n,
+                                     int *checkType)
+{
+  /* reference XzIn.c:141-224 (footer, locate) and :71-114 (index records) */
+  size_t end = srcLen;
+  *n = 0; *checkType = 0;
+  if ((end & 3) != 0 || end < 12) return SZ_ERROR_NO_ARCHIVE;
+  if (memcmp(src + end - 2, "YZ", 2) != 0)
+  {
+    while (end > 0 && src[end - 1] == 0) end--;
+    if ((end & 3) != 0 || end < 12 || memcmp(src + end - 2, "YZ", 2) != 0) return SZ_ERROR_NO_ARCHIVE;
+  }
+  const Byte *foot = src + end - 12;
+  const unsigned flags = ((unsigned)foot[8] << 8) | foot[9];
+  if (flags > 0xF) return SZ_ERROR_UNSUPPORTED;
+  if (lzb_le32(foot) != small_crc32(foot + 4, 6)) return SZ_ERROR_ARCHIVE;
+  const size_t idx_size = ((size_t)lzb_le32(foot + 4) + 1) << 2;
+  if (idx_size + 12 > end) return SZ_ERROR_NO_ARCHIVE;
+  const size_t idx_off = end - 12 - idx_size;
+  const Byte *idx = src + idx_off;
+  if (idx_size < 5 || idx[0] != 0) return SZ_ERROR_ARCHIVE;
+  if (small_crc32(idx, idx_size - 4) != lzb_le32(idx + idx_size - 4)) return SZ_ERROR_ARCHIVE;
+  size_t pos = 1;
+  UInt64 v;
+  unsigned s = Xz_ReadVarInt(idx + pos, idx_size - 4 - pos, &v);
+  if (!s) return SZ_ERROR_ARCHIVE;
+  pos += s;
+  const size_t nb = (size_t)v;
+  if (nb != v || nb * 2 > idx_size - 4) return SZ_ERROR_ARCHIVE;
+  const unsigned csz = XzFlags_GetCheckSize((CXzStreamFlags)flags);
+  std::vector<UInt64> total(nb), unpack(nb);
+  uint64_t data_total = 0;
+  for (size_t i = 0; i < nb; i++)
+  {
+    s = Xz_ReadVarInt(idx + pos, idx_size - 4 - pos, &total[i]);
+    if (!s) return SZ_ERROR_ARCHIVE;
+    pos += s;
+    s = Xz_ReadVarInt(idx + pos, idx_size - 4 - pos, &unpack[i]);
+    if (!s) return SZ_ERROR_ARCHIVE;
+    pos += s;
+    if (total[i] == 0) return SZ_ERROR_ARCHIVE;
+    data_total += (total[i] + 3) & ~(UInt64)3;
+  }
+  while ((pos & 3) != 0) if (idx[pos++] != 0) return SZ_ERROR_ARCHIVE;
+  if (pos != idx_size - 4) return SZ_ERROR_ARCHIVE;
+  if (12 + data_total > idx_off) return SZ_ERROR_ARCHIVE;
+  size_t cur = idx_off - (size_t)data_total - 12;
+  if (memcmp(src + cur, k_xz_magic, 6) != 0) return SZ_ERROR_NO_ARCHIVE;
+  CXzStreamFlags hflags;
+  SRes r = Xz_ParseHeader(&hflags, src + cur);
+  if (r != SZ_OK) return r;
+  if (hflags != flags) return SZ_ERROR_ARCHIVE;
+  *checkType = (int)(flags & 0xF);
+  *n = nb;
+  cur += 12;
+  for (size_t i = 0; i < nb && i < maxBlocks; i++)
+  {
+    LzbXzBlock &b = blocks[i];
+    memset(&b, 0, sizeof b);
+    if (src[cur] == 0) return SZ_ERROR_ARCHIVE;
+    const UInt32 hs = ((UInt32)src[cur] << 2) + 4;
+    if (hs + csz > total[i]) return SZ_ERROR_ARCHIVE;
+    XzFilterSpec fs[4];
+    int nf = 0;
+    r = parse_block_header(src + cur, fs, &nf);
+    if (r != SZ_OK) return r;
+    r = classify_chain(fs, nf, &b);
+    if (r != SZ_OK) return r;
+    b.hdr_off = cur; b.hdr_size = hs; b.data_off = cur + hs;
+    b.pack_size = total[i] - hs - csz; b.unpack_size = unpack[i];
+    b.check_off = b.data_off + ((b.pack_size + 3) & ~(uint64_t)3);
+    b.check_type = (uint8_t)(flags & 0xF);
+    b.expect = csz == 4 ? lzb_le32(src + b.check_off) : (csz == 8 ? lzb_le64(src + b.check_off) : 0);
+    b.complete = 1;
+    cur += (size_t)((total[i] + 3) & ~(UInt64)3);
+  }
+  return SZ_OK;
+}
+
+/* ------------------------------------------------------------------ XzUnpacker object --------- */
+struct XzUnpackerState
+{
+  uint64_t magic;
+  uint64_t num_blocks;
+  int finished;
+  int started;
+};
+#define XZU_MAGIC 0x4C5A42585A553031ull
+
+extern "C" SRes XzUnpacker_Create(CXzUnpacker *p, ISzAlloc *alloc)
+{
+  (void)alloc;
+  XzUnpackerState *s = (XzUnpackerState *)p;
+  memset(p, 0, sizeof *p);
+  s->magic = XZU_MAGIC;
+  return SZ_OK;
+}
+extern "C" void XzUnpacker_Free(CXzUnpacker *p) { (void)p; }
+extern "C" Bool XzUnpacker_IsStreamWasFinished(CXzUnpacker *p) { return ((XzUnpackerState *)p)->finished; }
+extern "C" UInt64 XzUnpacker_GetNumBlocks(const CXzUnpacker *p) { return ((const XzUnpackerState *)p)->num_blocks; }
+
+extern "C" SRes XzUnpacker_Code(CXzUnpacker *p, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
+                                int finishMode, ECoderStatus *status)
+{
+  (void)finishMode;
+  XzUnpackerState *s = (XzUnpackerState *)p;
+  if (s->magic != XZU_MAGIC) { *destLen = *srcLen = 0; return SZ_ERROR_PARAM; }
+  if (*srcLen == 0)
+  {
+    *destLen = 0;
+    *status = CODER_STATUS_NEEDS_MORE_INPUT;          /* reference XzDec.c:659-663 */
+    return SZ_OK;
+  }
+  if (s->started && !s->finished)
+  {
+    lzb_set_error("XzUnpacker_Code: resuming inside a stream is not supported in this round (present whole streams)");
+    *destLen = *srcLen = 0;
+    return SZ_ERROR_UNSUPPORTED;
+  }
+  UInt64 nb = 0;
+  int fin = 0;
+  SRes r = XzDecodeParallel(nullptr, dest, destLen, src, srcLen, status, &nb, &fin);
+  s->started = 1;
+  s->num_blocks += nb;
+  s->finished = fin;
+  return r;
+}

@@ -1,0 +1,571 @@
+/* lzb_host.cu -- host side of the C-ABI (include/lzb200.h): context, staging, batch entry points and
+ * the one-call SDK functions.  Host code is plain C-style C++ over the CUDA runtime; no torch types.
+ *
+ * Data path of Lzb_DecodeUnitsHost (the call behind LzmaUncompressBatch and the parallel LZMA2 / xz
+ * front ends): units are cut into slices; slice k goes H2D -> fused decode kernel -> D2H on stream
+ * k % 3, so the copies of one slice overlap the kernels of its neighbours.
+ */
+#include "lzb_host.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+/* ------------------------------------------------------------------ errors ----------------- */
+static thread_local char g_err[512] = "";
+
+void lzb_set_error(const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *Lzb_LastError(void) { return g_err; }
+
+bool lzb_cuda_ok(cudaError_t e, const char *what)
+{
+  if (e == cudaSuccess) return true;
+  lzb_set_error("%s: %s", what, cudaGetErrorString(e));
+  return false;
+}
+
+/* ------------------------------------------------------------------ context ---------------- */
+extern "C" LzbContext *Lzb_Create(int device)
+{
+  int count = 0;
+  if (!lzb_cuda_ok(cudaGetDeviceCount(&count), "cudaGetDeviceCount") || count == 0)
+  {
+    if (count == 0) lzb_set_error("no CUDA device: liblzb200 has no CPU fallback");
+    return nullptr;
+  }
+  if (device < 0 || device >= count) { lzb_set_error("device %d out of range (%d present)", device, count); return nullptr; }
+  if (!lzb_cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return nullptr;
+  LzbContext *c = new LzbContext();
+  c->device = device;
+  cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
+  for (int i = 0; i < LZB_SLOTS; i++)
+  {
+    if (!lzb_cuda_ok(cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !lzb_cuda_ok(cudaMalloc(&c->slot[i].d_ticket, 256), "cudaMalloc ticket"))
+    {
+      Lzb_Destroy(c);
+      return nullptr;
+    }
+  }
+  return c;
+}
+
+extern "C" void Lzb_Destroy(LzbContext *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < LZB_SLOTS; i++)
+  {
+    LzbSlot &s = c->slot[i];
+    if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    cudaFree(s.d_packed); cudaFree(s.d_out); cudaFree(s.d_units); cudaFree(s.d_results);
+    cudaFree(s.d_ticket); cudaFree(s.d_slab);
+    if (s.h_units) cudaFreeHost(s.h_units);
+    if (s.h_results) cudaFreeHost(s.h_results);
+  }
+  delete c;
+}
+
+extern "C" int Lzb_DeviceSMs(LzbContext *c) { return c ? c->sms : 0; }
+
+extern "C" void *Lzb_HostAlloc(size_t bytes)
+{
+  void *p = nullptr;
+  if (!lzb_cuda_ok(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault), "cudaHostAlloc")) return nullptr;
+  return p;
+}
+extern "C" void Lzb_HostFree(void *p) { if (p) cudaFreeHost(p); }
+
+static std::mutex g_default_mu;
+static LzbContext *g_default = nullptr;
+
+LzbContext *lzb_default_context()
+{
+  std::lock_guard<std::mutex> g(g_default_mu);
+  if (!g_default)
+  {
+    const char *e = getenv("LZB_DEVICE");
+    g_default = Lzb_Create(e ? atoi(e) : 0);
+  }
+  return g_default;
+}
+
+template <class T> static bool grow(T *&p, size_t &cap, size_t need, const char *what)
+{
+  if (need <= cap) return true;
+  cudaFree(p);
+  p = nullptr; cap = 0;
+  size_t want = need + need / 8 + 256;
+  if (!lzb_cuda_ok(cudaMalloc((void **)&p, want * sizeof(T)), what)) return false;
+  cap = want;
+  return true;
+}
+
+bool lzb_slot_reserve(LzbContext *c, LzbSlot &s, size_t packed, size_t out, size_t units, size_t slab)
+{
+  (void)c;
+  if (!grow(s.d_packed, s.packed_cap, packed + 64, "cudaMalloc packed arena")) return false;
+  if (!grow(s.d_out, s.out_cap, out + 64, "cudaMalloc output arena")) return false;
+  if (units > s.units_cap)
+  {
+    cudaFree(s.d_units); cudaFree(s.d_results);
+    s.d_units = nullptr; s.d_results = nullptr; s.units_cap = 0;
+    size_t want = units + units / 8 + 64;
+    if (!lzb_cuda_ok(cudaMalloc((void **)&s.d_units, want * sizeof(LzbUnit)), "cudaMalloc units")) return false;
+    if (!lzb_cuda_ok(cudaMalloc((void **)&s.d_results, want * sizeof(LzbResult)), "cudaMalloc results")) return false;
+    s.units_cap = want;
+  }
+  if (units > s.h_units_cap)
+  {
+    if (s.h_units) cudaFreeHost(s.h_units);
+    if (s.h_results) cudaFreeHost(s.h_results);
+    s.h_units = nullptr; s.h_results = nullptr; s.h_units_cap = 0;
+    size_t want = units + units / 8 + 64;
+    if (!lzb_cuda_ok(cudaHostAlloc((void **)&s.h_units, want * sizeof(LzbUnit), cudaHostAllocDefault), "cudaHostAlloc units")) return false;
+    if (!lzb_cuda_ok(cudaHostAlloc((void **)&s.h_results, want * sizeof(LzbResult), cudaHostAllocDefault), "cudaHostAlloc results")) return false;
+    s.h_units_cap = want;
+  }
+  if (slab && !grow(s.d_slab, s.slab_cap, slab, "cudaMalloc model slab")) return false;
+  return true;
+}
+
+/* probability-model bytes needed by a set of units (upper bound: monotone in lc+lp and pb).
+ * LZMA2 units carry the walker's maxima in lc (= max lc+lp) and pb. */
+static uint32_t model_bytes_for(const LzbUnit *u, size_t n)
+{
+  unsigned lclp = 0, pb = 0;
+  for (size_t i = 0; i < n; i++)
+  {
+    unsigned a = (unsigned)u[i].lc + u[i].lp;
+    if (a > lclp) lclp = a;
+    if (u[i].pb > pb) pb = u[i].pb;
+  }
+  return lzb_num_probs(lclp, 0, pb) * 2u;
+}
+
+static size_t slab_bytes_for(uint32_t model_bytes)
+{
+  uint32_t w, ctas, region; int shared_model;
+  if (lzb_launch_geometry(model_bytes, &w, &ctas, &region, &shared_model) != 0) return 0;
+  return shared_model ? 0 : (size_t)w * ctas * region;
+}
+
+/* ------------------------------------------------------------------ device-resident batch ---- */
+extern "C" SRes Lzb_DecodeUnitsDevice(LzbContext *c, const Byte *d_packed, Byte *d_out, const LzbUnit *d_units,
+                                      LzbResult *d_results, size_t n, unsigned maxLcLp, unsigned maxPb, void *stream)
+{
+  if (!c) { lzb_set_error("null context"); return SZ_ERROR_PARAM; }
+  if (n > 0xFFFFFFFFull) return SZ_ERROR_PARAM;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
+  LzbSlot &s = c->slot[0];
+  const uint32_t model = lzb_num_probs(maxLcLp, 0, maxPb) * 2u;
+  const size_t slab = slab_bytes_for(model);
+  if (slab && !grow(s.d_slab, s.slab_cap, slab, "cudaMalloc model slab")) return SZ_ERROR_MEM;
+  cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+  int rc = lzb_launch_decode(d_packed, d_out, d_units, d_results, (uint32_t)n, s.d_ticket, model, s.d_slab, st);
+  if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+  return SZ_OK;
+}
+
+/* ------------------------------------------------------------------ host-arena batch --------- */
+struct Slice { size_t first, count; uint64_t src_lo, src_hi, dst_lo, dst_hi; };
+
+static void make_slices(const LzbUnit *u, size_t n, std::vector<Slice> &out)
+{
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; i++) total += u[i].dst_cap;
+  uint64_t target = total / 8;
+  if (target < (64ull << 20)) target = 64ull << 20;
+  if (target > (1ull << 30)) target = 1ull << 30;
+  size_t i = 0;
+  while (i < n)
+  {
+    Slice s;
+    s.first = i; s.count = 0;
+    s.src_lo = s.dst_lo = ~0ull; s.src_hi = s.dst_hi = 0;
+    uint64_t acc = 0;
+    while (i < n && (s.count == 0 || acc < target))
+    {
+      const LzbUnit &x = u[i];
+      /* keep the slice's arena windows tight: stop when a unit jumps far away from the window */
+      uint64_t nlo = std::min<uint64_t>(s.src_lo, x.src_off), nhi = std::max<uint64_t>(s.src_hi, x.src_off + x.src_len);
+      uint64_t dlo = std::min<uint64_t>(s.dst_lo, x.dst_off), dhi = std::max<uint64_t>(s.dst_hi, x.dst_off + x.dst_cap);
+      if (s.count != 0 && ((nhi - nlo) > 4 * target + (64ull << 20) || (dhi - dlo) > 4 * target + (64ull << 20))) break;
+      s.src_lo = nlo; s.src_hi = nhi; s.dst_lo = dlo; s.dst_hi = dhi;
+      acc += x.dst_cap;
+      s.count++; i++;
+    }
+    out.push_back(s);
+  }
+}
+
+extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+                                    const LzbUnit *units, LzbResult *results, size_t n)
+{
+  if (!c) { lzb_set_error("null context"); return SZ_ERROR_PARAM; }
+  if (n == 0) return SZ_OK;
+  for (size_t i = 0; i < n; i++)
+    if (units[i].src_off + units[i].src_len > packedBytes || units[i].dst_off + units[i].dst_cap > outBytes)
+    { lzb_set_error("unit %zu exceeds its arena", i); return SZ_ERROR_PARAM; }
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
+
+  const uint32_t model = model_bytes_for(units, n);
+  const size_t slab = slab_bytes_for(model);
+  std::vector<Slice> slices;
+  make_slices(units, n, slices);
+
+  SRes ret = SZ_OK;
+  std::vector<int> pending_slot(LZB_SLOTS, -1);          /* slice index in flight on each slot */
+
+  auto drain = [&](int si) -> bool
+  {
+    int k = pending_slot[si];
+    if (k < 0) return true;
+    LzbSlot &s = c->slot[si];
+    if (!lzb_cuda_ok(cudaStreamSynchronize(s.stream), "decode slice")) return false;
+    memcpy(results + slices[k].first, s.h_results, slices[k].count * sizeof(LzbResult));
+    pending_slot[si] = -1;
+    return true;
+  };
+
+  for (size_t k = 0; k < slices.size() && ret == SZ_OK; k++)
+  {
+    const int si = (int)(k % LZB_SLOTS);
+    LzbSlot &s = c->slot[si];
+    const Slice &sl = slices[k];
+    if (!drain(si)) { ret = SZ_ERROR_FAIL; break; }
+    const size_t pbytes = (size_t)(sl.src_hi - sl.src_lo), obytes = (size_t)(sl.dst_hi - sl.dst_lo);
+    if (!lzb_slot_reserve(c, s, pbytes, obytes, sl.count, slab)) { ret = SZ_ERROR_MEM; break; }
+    for (size_t j = 0; j < sl.count; j++)
+    {
+      s.h_units[j] = units[sl.first + j];
+      s.h_units[j].src_off -= sl.src_lo;
+      s.h_units[j].dst_off -= sl.dst_lo;
+    }
+    bool ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_packed, packed + sl.src_lo, pbytes, cudaMemcpyHostToDevice, s.stream), "H2D packed") &&
+              lzb_cuda_ok(cudaMemcpyAsync(s.d_units, s.h_units, sl.count * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D units");
+    if (!ok) { ret = SZ_ERROR_FAIL; break; }
+    int rc = lzb_launch_decode(s.d_packed, s.d_out, s.d_units, s.d_results, (uint32_t)sl.count, s.d_ticket, model, s.d_slab, s.stream);
+    if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); ret = SZ_ERROR_FAIL; break; }
+    /* D2H: one copy per maximal run of units whose outputs tile the arena (never touch the gaps) */
+    size_t j = 0;
+    while (j < sl.count && ok)
+    {
+      uint64_t lo = units[sl.first + j].dst_off, hi = lo + units[sl.first + j].dst_cap;
+      size_t e = j + 1;
+      while (e < sl.count && units[sl.first + e].dst_off == hi) { hi += units[sl.first + e].dst_cap; e++; }
+      if (hi > lo)
+        ok = lzb_cuda_ok(cudaMemcpyAsync(out + lo, s.d_out + (lo - sl.dst_lo), (size_t)(hi - lo), cudaMemcpyDeviceToHost, s.stream), "D2H output");
+      j = e;
+    }
+    ok = ok && lzb_cuda_ok(cudaMemcpyAsync(s.h_results, s.d_results, sl.count * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results");
+    if (!ok) { ret = SZ_ERROR_FAIL; break; }
+    pending_slot[si] = (int)k;
+  }
+  for (int si = 0; si < LZB_SLOTS; si++)
+    if (!drain(si)) ret = SZ_ERROR_FAIL;
+  return ret;
+}
+
+SRes lzb_decode_host_simple(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+                            const LzbUnit *units, LzbResult *results, size_t n)
+{
+  return Lzb_DecodeUnitsHost(c, packed, packedBytes, out, outBytes, units, results, n);
+}
+
+/* ------------------------------------------------------------------ props ------------------- */
+extern "C" SRes LzmaProps_Decode(CLzmaProps *p, const Byte *data, unsigned size)
+{
+  /* reference LzmaDec.c:898-922: dictionary clamped up to 4 KiB, d < 225 */
+  if (size < LZMA_PROPS_SIZE) return SZ_ERROR_UNSUPPORTED;
+  UInt32 dict = lzb_le32(data + 1);
+  p->dicSize = dict < (1u << 12) ? (1u << 12) : dict;
+  unsigned d = data[0];
+  if (d >= 9 * 5 * 5) return SZ_ERROR_UNSUPPORTED;
+  p->lc = d % 9; d /= 9;
+  p->pb = d / 5;
+  p->lp = d % 5;
+  return SZ_OK;
+}
+
+/* ------------------------------------------------------------------ one-call raw LZMA -------- */
+extern "C" SRes LzmaDecode(Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen, const Byte *propData,
+                           unsigned propSize, ELzmaFinishMode finishMode, ELzmaStatus *status, ISzAlloc *alloc)
+{
+  /* reference LzmaDec.c:972-1002.  `alloc` is accepted for signature compatibility; the model lives in
+   * device memory, so nothing is requested from it. */
+  (void)alloc;
+  const SizeT inSize = *srcLen, outSize = *destLen;
+  *srcLen = *destLen = 0;
+  if (inSize < 5) return SZ_ERROR_INPUT_EOF;
+  CLzmaProps pr;
+  SRes r = LzmaProps_Decode(&pr, propData, propSize);
+  if (r != SZ_OK) return r;
+  if (inSize > 0xFFFFFFFFull || outSize > 0xFFFFFFFFull) { lzb_set_error("single stream larger than 4 GiB"); return SZ_ERROR_UNSUPPORTED; }
+  LzbContext *c = lzb_default_context();
+  if (!c) return SZ_ERROR_FAIL;
+  LzbUnit u;
+  memset(&u, 0, sizeof u);
+  u.src_len = (uint32_t)inSize; u.dst_cap = (uint32_t)outSize; u.dict_size = pr.dicSize;
+  u.codec = LZB_CODEC_LZMA; u.lc = (uint8_t)pr.lc; u.lp = (uint8_t)pr.lp; u.pb = (uint8_t)pr.pb;
+  u.finish = (uint8_t)finishMode;
+  LzbResult res;
+  r = Lzb_DecodeUnitsHost(c, src, inSize, dest, outSize, &u, &res, 1);
+  if (r != SZ_OK) return r;
+  *srcLen = res.src_used;
+  *destLen = res.dst_done;
+  *status = (ELzmaStatus)res.status;
+  return res.res;
+}
+
+extern "C" int LzmaUncompress(unsigned char *dest, size_t *destLen, const unsigned char *src, SizeT *srcLen,
+                              const unsigned char *props, size_t propsSize)
+{
+  /* reference LzmaLib.c:41-46 */
+  ELzmaStatus status;
+  return LzmaDecode(dest, destLen, src, srcLen, props, (unsigned)propsSize, LZMA_FINISH_ANY, &status, nullptr);
+}
+
+extern "C" SRes LzmaUncompressBatch(LzbContext *c, size_t n, unsigned char *const *dest, size_t *destLen,
+                                    const unsigned char *const *src, size_t *srcLen, const unsigned char *props,
+                                    size_t propsStride, SRes *res)
+{
+  if (!c) c = lzb_default_context();
+  if (!c) return SZ_ERROR_FAIL;
+  if (n == 0) return SZ_OK;
+  /* gather the scattered streams into pinned arenas (callers that already hold arenas use
+   * Lzb_DecodeUnitsHost directly and skip this copy) */
+  std::vector<LzbUnit> units(n);
+  std::vector<LzbResult> results(n);
+  size_t pin = 0, pout = 0;
+  for (size_t i = 0; i < n; i++)
+  {
+    res[i] = SZ_OK;
+    CLzmaProps pr;
+    SRes r = LzmaProps_Decode(&pr, props + i * propsStride, LZMA_PROPS_SIZE);
+    LzbUnit &u = units[i];
+    memset(&u, 0, sizeof u);
+    if (srcLen[i] < 5) r = SZ_ERROR_INPUT_EOF;              /* LzmaDec.c:981-982 precedes the props check */
+    else if (r == SZ_OK && (srcLen[i] > 0xFFFFFFFFull || destLen[i] > 0xFFFFFFFFull)) r = SZ_ERROR_UNSUPPORTED;
+    if (r != SZ_OK) { res[i] = r; u.flags = 0x80; continue; }   /* 0x80: skipped on the host */
+    u.src_off = pin; u.src_len = (uint32_t)srcLen[i];
+    u.dst_off = pout; u.dst_cap = (uint32_t)destLen[i];
+    u.dict_size = pr.dicSize; u.codec = LZB_CODEC_LZMA;
+    u.lc = (uint8_t)pr.lc; u.lp = (uint8_t)pr.lp; u.pb = (uint8_t)pr.pb; u.finish = LZMA_FINISH_ANY;
+    pin += (srcLen[i] + 15) & ~(size_t)15;
+    pout += (destLen[i] + 15) & ~(size_t)15;
+  }
+  Byte *hin = (Byte *)Lzb_HostAlloc(pin + 16), *hout = (Byte *)Lzb_HostAlloc(pout + 16);
+  if (!hin || !hout) { Lzb_HostFree(hin); Lzb_HostFree(hout); return SZ_ERROR_MEM; }
+  std::vector<LzbUnit> run;
+  std::vector<size_t> map;
+  run.reserve(n); map.reserve(n);
+  for (size_t i = 0; i < n; i++)
+    if (!(units[i].flags & 0x80)) { memcpy(hin + units[i].src_off, src[i], srcLen[i]); run.push_back(units[i]); map.push_back(i); }
+  SRes r = Lzb_DecodeUnitsHost(c, hin, pin + 16, hout, pout + 16, run.data(), results.data(), run.size());
+  if (r == SZ_OK)
+  {
+    for (size_t k = 0; k < run.size(); k++)
+    {
+      size_t i = map[k];
+      res[i] = results[k].res;
+      srcLen[i] = results[k].src_used;
+      destLen[i] = results[k].dst_done;
+      memcpy(dest[i], hout + run[k].dst_off, results[k].dst_done);
+    }
+    for (size_t i = 0; i < n; i++)
+      if (units[i].flags & 0x80) { srcLen[i] = 0; destLen[i] = 0; }
+  }
+  Lzb_HostFree(hin); Lzb_HostFree(hout);
+  return r;
+}
+
+/* ------------------------------------------------------------------ checks (GPU) ------------- */
+/* GF(2)[x]/P arithmetic on the host, only to stitch per-segment registers (reflected bit order) */
+static uint32_t mul32(uint32_t a, uint32_t b)
+{
+  uint32_t p = 0;
+  for (int k = 0; k < 32; k++) { if ((a >> (31 - k)) & 1) p ^= b; b = (b >> 1) ^ (0xEDB88320u & (0u - (b & 1))); }
+  return p;
+}
+static uint64_t mul64(uint64_t a, uint64_t b)
+{
+  uint64_t p = 0;
+  for (int k = 0; k < 64; k++) { if ((a >> (63 - k)) & 1) p ^= b; b = (b >> 1) ^ (0xC96C5795D7870F42ull & (0ull - (b & 1))); }
+  return p;
+}
+uint32_t lzb_crc32_shift(uint32_t reg, uint64_t n)
+{
+  uint32_t r = 1u << 31, sq = 1u << 23;
+  for (; n; n >>= 1) { if (n & 1) r = mul32(r, sq); sq = mul32(sq, sq); }
+  return mul32(reg, r);
+}
+uint64_t lzb_crc64_shift(uint64_t reg, uint64_t n)
+{
+  uint64_t r = 1ull << 63, sq = 1ull << 55;
+  for (; n; n >>= 1) { if (n & 1) r = mul64(r, sq); sq = mul64(sq, sq); }
+  return mul64(reg, r);
+}
+
+UInt32 g_CrcTable[256 * 8];
+UInt64 g_Crc64Table[256];
+
+extern "C" void CrcGenerateTable(void)
+{
+  /* reference 7zCrc.c:49-74: the tables are part of the exported data, so they are still produced;
+   * the GPU path does not read them (each warp builds its own copy in shared memory). */
+  for (UInt32 i = 0; i < 256; i++)
+  {
+    UInt32 r = i;
+    for (int j = 0; j < 8; j++) r = (r >> 1) ^ (0xEDB88320u & ~((r & 1) - 1));
+    g_CrcTable[i] = r;
+  }
+  for (UInt32 i = 256; i < 256 * 8; i++)
+  {
+    UInt32 r = g_CrcTable[i - 256];
+    g_CrcTable[i] = g_CrcTable[r & 0xFF] ^ (r >> 8);
+  }
+}
+
+extern "C" void Crc64GenerateTable(void)
+{
+  for (UInt32 i = 0; i < 256; i++)
+  {
+    UInt64 r = i;
+    for (int j = 0; j < 8; j++) r = (r >> 1) ^ (0xC96C5795D7870F42ull & ~((r & 1) - 1));
+    g_Crc64Table[i] = r;
+  }
+}
+
+/* finalized digest of a host buffer, computed on the GPU in 1 MiB segments (one warp each) */
+static bool gpu_digest(const void *data, size_t size, int kind, uint64_t *digest)
+{
+  LzbContext *c = lzb_default_context();
+  if (!c) return false;
+  const size_t seg = 1u << 20;
+  const size_t n = size ? (size + seg - 1) / seg : 1;
+  std::vector<LzbUnit> units(n);
+  std::vector<LzbResult> results(n);
+  for (size_t i = 0; i < n; i++)
+  {
+    memset(&units[i], 0, sizeof(LzbUnit));
+    units[i].dst_off = i * seg;
+    units[i].dst_cap = (uint32_t)std::min(seg, size - i * seg);
+    units[i].check = (uint8_t)kind;
+  }
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
+  LzbSlot &s = c->slot[0];
+  if (!lzb_slot_reserve(c, s, 0, size, n, 0)) return false;
+  bool ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_out, data, size, cudaMemcpyHostToDevice, s.stream), "H2D data") &&
+            lzb_cuda_ok(cudaMemcpyAsync(s.d_units, units.data(), n * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D units");
+  if (!ok) return false;
+  int rc = lzb_launch_post_only(s.d_out, s.d_units, s.d_results, (uint32_t)n, s.stream);
+  if (rc != 0) { lzb_set_error("post launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return false; }
+  ok = lzb_cuda_ok(cudaMemcpyAsync(results.data(), s.d_results, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results") &&
+       lzb_cuda_ok(cudaStreamSynchronize(s.stream), "digest kernel");
+  if (!ok) return false;
+  /* crc(A||B) = shift(crc(A), |B|) ^ crc(B) for finalized values (preset/inversion cancel out) */
+  uint64_t acc = 0;
+  for (size_t i = 0; i < n; i++)
+  {
+    const uint64_t len = units[i].dst_cap;
+    acc = (kind == LZB_CHECK_CRC32 ? (uint64_t)lzb_crc32_shift((uint32_t)acc, len) : lzb_crc64_shift(acc, len)) ^ results[i].check;
+  }
+  *digest = acc;
+  return true;
+}
+
+extern "C" UInt32 CrcCalc(const void *data, size_t size)
+{
+  uint64_t d = 0;
+  if (!gpu_digest(data, size, LZB_CHECK_CRC32, &d)) return 0;
+  return (UInt32)d;
+}
+extern "C" UInt32 CrcUpdate(UInt32 v, const void *data, size_t size)
+{
+  /* register after `data` starting from register v:  shift(v ^ ~0, n) ^ crc(data) ^ ~0 */
+  uint64_t d = 0;
+  if (!gpu_digest(data, size, LZB_CHECK_CRC32, &d)) return v;
+  return lzb_crc32_shift(v ^ 0xFFFFFFFFu, size) ^ (UInt32)d ^ 0xFFFFFFFFu;
+}
+extern "C" UInt64 Crc64Calc(const void *data, size_t size)
+{
+  uint64_t d = 0;
+  if (!gpu_digest(data, size, LZB_CHECK_CRC64, &d)) return 0;
+  return d;
+}
+extern "C" UInt64 Crc64Update(UInt64 v, const void *data, size_t size)
+{
+  uint64_t d = 0;
+  if (!gpu_digest(data, size, LZB_CHECK_CRC64, &d)) return v;
+  return lzb_crc64_shift(~v, size) ^ d ^ ~0ull;
+}
+
+/* ------------------------------------------------------------------ filters (GPU) ------------ */
+static bool gpu_filter(Byte *data, size_t size, int filter, uint32_t param, uint8_t flags = 0, uint64_t aux = 0,
+                       LzbResult *res_out = nullptr)
+{
+  LzbContext *c = lzb_default_context();
+  if (!c) return false;
+  if (size > 0xFFFFFFFFull) { lzb_set_error("filter buffer larger than 4 GiB"); return false; }
+  LzbUnit u;
+  LzbResult r;
+  memset(&u, 0, sizeof u);
+  u.dst_cap = (uint32_t)size; u.filter = (uint8_t)filter; u.filter_param = param;
+  u.flags = flags; u.expect = aux;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
+  LzbSlot &s = c->slot[0];
+  if (!lzb_slot_reserve(c, s, 0, size, 1, 0)) return false;
+  bool ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_out, data, size, cudaMemcpyHostToDevice, s.stream), "H2D data") &&
+            lzb_cuda_ok(cudaMemcpyAsync(s.d_units, &u, sizeof u, cudaMemcpyHostToDevice, s.stream), "H2D unit");
+  if (!ok) return false;
+  int rc = lzb_launch_post_only(s.d_out, s.d_units, s.d_results, 1, s.stream);
+  if (rc != 0) { lzb_set_error("post launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return false; }
+  ok = lzb_cuda_ok(cudaMemcpyAsync(data, s.d_out, size, cudaMemcpyDeviceToHost, s.stream), "D2H data") &&
+       lzb_cuda_ok(cudaMemcpyAsync(&r, s.d_results, sizeof r, cudaMemcpyDeviceToHost, s.stream), "D2H result") &&
+       lzb_cuda_ok(cudaStreamSynchronize(s.stream), "filter kernel");
+  if (ok && res_out) *res_out = r;
+  return ok;
+}
+
+extern "C" SizeT x86_Convert(Byte *data, SizeT size, UInt32 ip, UInt32 *state, int encoding)
+{
+  /* reference Bra86.c:11-85: both directions, history carried in *state, returns the bytes processed.
+   * One warp scans the buffer in 32 segments that start at history-free positions (lzb_post.cuh). */
+  if (size < 5) return 0;
+  LzbResult r;
+  const uint8_t flags = (uint8_t)(4 | (encoding ? 2 : 0));
+  if (!gpu_filter(data, size, LZB_FILTER_X86, ip, flags, (uint64_t)(*state & 7) << 32, &r)) return 0;
+  *state = (UInt32)r.status;
+  return r.src_used;
+}
+
+extern "C" void Delta_Init(Byte *state) { memset(state, 0, DELTA_STATE_SIZE); }
+
+extern "C" void Delta_Decode(Byte *state, unsigned delta, Byte *data, SizeT size)
+{
+  /* reference Delta.c:43-62.  A non-zero incoming history is folded in on the host (it only affects
+   * the first `delta` bytes: out[i] = in[i] + hist[i]) before the GPU prefix-sum, and the outgoing
+   * history is the last `delta` outputs. */
+  if (size == 0) return;
+  for (unsigned i = 0; i < delta && i < size; i++) data[i] = (Byte)(data[i] + state[i]);
+  if (!gpu_filter(data, size, LZB_FILTER_DELTA, delta)) return;
+  Byte next[DELTA_STATE_SIZE];
+  if (size >= delta) memcpy(next, data + size - delta, delta);
+  else { memcpy(next, state + size, delta - size); memcpy(next + delta - size, data, size); }
+  memcpy(state, next, delta);
+}

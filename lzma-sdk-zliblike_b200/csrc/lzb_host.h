@@ -1,0 +1,53 @@
+/* lzb_host.h -- internals shared by the host translation units (context, staging, error text). */
+#ifndef LZB_HOST_H
+#define LZB_HOST_H
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/lzb200.h"
+#include "lzb_kernels.h"
+
+#define LZB_SLOTS 3
+
+struct LzbSlot
+{
+  cudaStream_t stream = nullptr;
+  uint8_t *d_packed = nullptr; size_t packed_cap = 0;
+  uint8_t *d_out = nullptr;    size_t out_cap = 0;
+  LzbUnit *d_units = nullptr;  LzbResult *d_results = nullptr; size_t units_cap = 0;
+  LzbUnit *h_units = nullptr;  LzbResult *h_results = nullptr; size_t h_units_cap = 0;   /* pinned */
+  uint32_t *d_ticket = nullptr;
+  uint8_t *d_slab = nullptr;   size_t slab_cap = 0;
+};
+
+struct LzbContext
+{
+  int device = 0;
+  int sms = 0;
+  LzbSlot slot[LZB_SLOTS];
+  std::mutex mu;
+};
+
+void lzb_set_error(const char *fmt, ...);
+bool lzb_cuda_ok(cudaError_t e, const char *what);
+LzbContext *lzb_default_context();                 /* lazily created; NULL (+ error text) without a GPU */
+bool lzb_slot_reserve(LzbContext *c, LzbSlot &s, size_t packed, size_t out, size_t units, size_t slab);
+
+/* run units through the fused kernel from host arenas (single slice, synchronous) */
+SRes lzb_decode_host_simple(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+                            const LzbUnit *units, LzbResult *results, size_t n);
+
+/* little helpers */
+static inline uint32_t lzb_le32(const Byte *p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static inline uint64_t lzb_le64(const Byte *p) { return (uint64_t)lzb_le32(p) | ((uint64_t)lzb_le32(p + 4) << 32); }
+
+/* host-side GF(2) helpers for stitching CRCs of independently processed segments */
+uint32_t lzb_crc32_shift(uint32_t reg, uint64_t nbytes);   /* reg * x^(8n) mod P32 */
+uint64_t lzb_crc64_shift(uint64_t reg, uint64_t nbytes);
+
+#endif

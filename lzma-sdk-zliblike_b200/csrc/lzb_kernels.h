@@ -1,0 +1,34 @@
+/* lzb_kernels.h -- launcher prototypes between lzb_kernels.cu and the host layer (lzb_host.cu). */
+#ifndef LZB_KERNELS_H
+#define LZB_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lzb_types.h"
+
+#define LZB_MAX_WARPS_PER_CTA 16
+#define LZB_MAX_SHARED_MODEL_BYTES (56u * 1024u)
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Residency the decode kernel will use for a given probability-model size (bytes). */
+int lzb_launch_geometry(uint32_t model_bytes, uint32_t *warps_per_cta, uint32_t *ctas, uint32_t *region_bytes,
+                        int *shared_model);
+
+/* Decode n_units units.  d_ticket: one uint32 of device scratch.  d_model_slab: only needed when the
+ * model does not fit shared memory (ctas * warps_per_cta * region_bytes bytes), else NULL. */
+int lzb_launch_decode(const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *d_units, LzbResult *d_results,
+                      uint32_t n_units, uint32_t *d_ticket, uint32_t model_bytes, uint8_t *d_model_slab,
+                      cudaStream_t stream);
+
+/* Filter/check only, over bytes already in device memory (dst_off/dst_cap/filter/check of each unit). */
+int lzb_launch_post_only(uint8_t *d_data, const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units,
+                         cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

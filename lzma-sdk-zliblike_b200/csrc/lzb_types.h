@@ -1,0 +1,77 @@
+/* lzb_types.h -- records shared by the host C-ABI layer and the sm_100a kernels.
+ *
+ * A UNIT is the independently decodable piece of work one warp owns:
+ *   raw LZMA stream (LzmaUncompress call), LZMA2 dictionary-reset group, or xz block.
+ * Vocabulary follows the reference (units/chunks/blocks/dictionary), not ML terms.
+ */
+#ifndef LZB_TYPES_H
+#define LZB_TYPES_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { LZB_CODEC_LZMA = 0, LZB_CODEC_LZMA2 = 1 };
+enum { LZB_FILTER_NONE = 0, LZB_FILTER_DELTA = 3, LZB_FILTER_X86 = 4 };   /* xz filter ids, Xz.h:11-19 */
+enum { LZB_CHECK_NONE = 0, LZB_CHECK_CRC32 = 1, LZB_CHECK_CRC64 = 4 };     /* xz check ids, Xz.h:66-69 */
+enum { LZB_UNIT_VERIFY = 1 };  /* flags: compare the computed digest with `expect` -> SZ_ERROR_CRC */
+
+typedef struct LzbUnit
+{
+  uint64_t src_off;       /* packed bytes start here in the packed arena            */
+  uint64_t dst_off;       /* output goes here in the output arena (also the window) */
+  uint32_t src_len;       /* packed bytes available                                 */
+  uint32_t dst_cap;       /* output capacity == dicLimit == dicBufSize              */
+  uint32_t dict_size;     /* LZMA dictionary size (match-distance validity)         */
+  uint8_t  codec;         /* LZB_CODEC_*                                            */
+  uint8_t  lc, lp, pb;    /* raw LZMA properties (LZMA2 reads them from chunks)     */
+  uint8_t  finish;        /* ELzmaFinishMode: 0 ANY, 1 END                          */
+  uint8_t  filter;        /* LZB_FILTER_* applied in place after decode             */
+  uint8_t  check;         /* LZB_CHECK_*  computed over the final bytes             */
+  uint8_t  flags;         /* LZB_UNIT_*                                             */
+  uint32_t filter_param;  /* delta distance (1..256) or x86 start offset            */
+  uint64_t expect;        /* stored digest, little-endian value                     */
+} LzbUnit;                /* 48 bytes */
+
+typedef struct LzbResult
+{
+  int32_t  res;           /* SRes (Types.h:25-41)                        */
+  int32_t  status;        /* ELzmaStatus (LzmaDec.h:100-107)             */
+  uint32_t src_used;      /* *srcLen on return                           */
+  uint32_t dst_done;      /* *destLen / dicPos on return                 */
+  uint64_t check;         /* computed digest (0 when check == NONE)      */
+} LzbResult;              /* 24 bytes */
+
+#define LZB_SZ_OK 0
+#define LZB_SZ_ERROR_DATA 1
+#define LZB_SZ_ERROR_MEM 2
+#define LZB_SZ_ERROR_CRC 3
+#define LZB_SZ_ERROR_UNSUPPORTED 4
+#define LZB_SZ_ERROR_PARAM 5
+#define LZB_SZ_ERROR_INPUT_EOF 6
+#define LZB_SZ_ERROR_OUTPUT_EOF 7
+#define LZB_SZ_ERROR_FAIL 11
+#define LZB_SZ_ERROR_ARCHIVE 16
+#define LZB_SZ_ERROR_NO_ARCHIVE 17
+
+#define LZB_ST_NOT_SPECIFIED 0
+#define LZB_ST_FINISHED_WITH_MARK 1
+#define LZB_ST_NOT_FINISHED 2
+#define LZB_ST_NEEDS_MORE_INPUT 3
+#define LZB_ST_MAYBE_FINISHED_WITHOUT_MARK 4
+
+/* Probability-model footprint for given properties (compact layout of lzb_core.cuh). */
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline uint32_t lzb_num_probs(unsigned lc, unsigned lp, unsigned pb)
+{
+  return 950u + (56u << pb) + (768u << (lc + lp));
+}
+
+#ifdef __cplusplus
+}
+#endif
+#endif

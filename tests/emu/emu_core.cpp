@@ -1,0 +1,50 @@
+/* emu_core.cpp -- TEST-ONLY host build of the device decode logic.
+ *
+ * Compiles lzma-sdk-zliblike_b200/csrc/lzb_core.cuh + lzb_post.cuh with -DLZB_EMU (one emulated lane)
+ * so that `pytest -m "not gpu"` can exercise the kernel's symbol grammar, finish-mode/lookahead
+ * driver and LZMA2 chunk machine against the oracle on machines without a GPU.  It is NOT a CPU
+ * fallback: nothing in the product package loads this library, and the product fails loudly when
+ * the CUDA library or a device is missing.
+ */
+#define LZB_EMU 1
+#include <stdlib.h>
+#include <vector>
+
+#include "lzb_core.cuh"
+#include "lzb_post.cuh"
+
+/* filter / check only, like lzb_post_only_kernel */
+extern "C" int emu_post_units(uint8_t *data, const LzbUnit *units, LzbResult *results, uint32_t n)
+{
+  std::vector<uint8_t> scratch(lzb::kPostScratchBytes);
+  for (uint32_t i = 0; i < n; i++)
+  {
+    const LzbUnit &u = units[i];
+    LzbResult r;
+    r.res = LZB_SZ_OK; r.status = LZB_ST_NOT_SPECIFIED; r.src_used = 0; r.dst_done = u.dst_cap; r.check = 0;
+    lzb::post_process(u, r, data + u.dst_off, scratch.data());
+    results[i] = r;
+  }
+  return 0;
+}
+
+extern "C" int emu_decode_units(const uint8_t *packed, uint8_t *out, const LzbUnit *units, LzbResult *results,
+                                uint32_t n)
+{
+  std::vector<uint16_t> probs;
+  std::vector<uint8_t> scratch(lzb::kPostScratchBytes);
+  for (uint32_t i = 0; i < n; i++)
+  {
+    const LzbUnit &u = units[i];
+    LzbResult r;
+    uint32_t np = u.codec == LZB_CODEC_LZMA2 ? lzb_num_probs(4, 0, 4) : lzb_num_probs(u.lc, u.lp, u.pb);
+    if (np * 2 < lzb::kPostScratchBytes) np = lzb::kPostScratchBytes / 2;
+    probs.assign(np, 0xDEAD);
+    lzb::UnitDecoder d;
+    d.begin(packed + u.src_off, u.src_len, out + u.dst_off, u.dst_cap, u.dict_size, probs.data());
+    lzb::decode_unit(d, u, r);
+    lzb::post_process(u, r, out + u.dst_off, (uint8_t *)probs.data());
+    results[i] = r;
+  }
+  return 0;
+}

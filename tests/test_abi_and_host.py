@@ -1,0 +1,146 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol
+include/lzb200.h declares, keeps the reference's public struct layouts, refuses to decode without a
+device (no CPU fallback), and its HOST-side front ends (property parsing, LZMA2 unit walk, xz index and
+varints) agree with the oracle.  No compute call is made here."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import lzb200
+from lzb200 import lib as L
+from lzb200 import records as R
+
+
+class CLzmaProps(C.Structure):
+    _fields_ = [("lc", C.c_uint), ("lp", C.c_uint), ("pb", C.c_uint), ("dicSize", C.c_uint32)]
+
+
+class CLzmaDec(C.Structure):          # reference LzmaDec.h:50-69
+    _fields_ = [("prop", CLzmaProps), ("probs", C.c_void_p), ("dic", C.c_void_p), ("buf", C.c_void_p),
+                ("range", C.c_uint32), ("code", C.c_uint32), ("dicPos", C.c_size_t), ("dicBufSize", C.c_size_t),
+                ("processedPos", C.c_uint32), ("checkDicSize", C.c_uint32), ("state", C.c_uint),
+                ("reps", C.c_uint32 * 4), ("remainLen", C.c_uint), ("needFlush", C.c_int), ("needInitState", C.c_int),
+                ("numProbs", C.c_uint32), ("tempBufSize", C.c_uint), ("tempBuf", C.c_uint8 * 20)]
+
+
+class CLzma2Dec(C.Structure):         # reference Lzma2Dec.h:15-25
+    _fields_ = [("decoder", CLzmaDec), ("packSize", C.c_uint32), ("unpackSize", C.c_uint32), ("state", C.c_int),
+                ("control", C.c_uint8), ("needInitDic", C.c_int), ("needInitState", C.c_int), ("needInitProp", C.c_int)]
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = L.load()
+    names = [n for n in L.declared_symbols() if n != "void"]
+    assert len(names) >= 45
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_public_struct_layouts_match_reference_abi():
+    # SURVEY.md §8b (measured on the reference): sizeof 136 / 168 / 1792 and the field offsets
+    assert C.sizeof(CLzmaDec) == 136 and C.sizeof(CLzma2Dec) == 168
+    offs = {f: getattr(CLzmaDec, f).offset for f, _ in CLzmaDec._fields_}
+    assert offs == dict(prop=0, probs=16, dic=24, buf=32, range=40, code=44, dicPos=48, dicBufSize=56,
+                        processedPos=64, checkDicSize=68, state=72, reps=76, remainLen=92, needFlush=96,
+                        needInitState=100, numProbs=104, tempBufSize=108, tempBuf=112)
+    assert CLzma2Dec.packSize.offset == 136 and CLzma2Dec.needInitProp.offset == 160
+    hdr = open(L.HEADER).read()
+    assert "UInt64 opaque[224]" in hdr           # CXzUnpacker storage = 1792 bytes like the reference's
+    assert R.UNIT_DTYPE.itemsize == 48 and R.RESULT_DTYPE.itemsize == 24
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(L.LzbError) as e:
+        L.Context(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+    blobs, cs = cases.golden()
+    c = cases.cases_of("lzma")[0]
+    with pytest.raises(L.LzbError):
+        lzb200.sdk.lzma_decode(blobs[c["blob"]], bytes.fromhex(c["props"]), c["cap"], 0)
+
+
+def test_props_decode():
+    lib = L.load()
+    p = CLzmaProps()
+    for d in range(0, 256, 7):
+        raw = bytes([d, 0x34, 0x12, 0, 0])
+        r = lib.LzmaProps_Decode(C.byref(p), raw, 5)
+        if d >= 225:
+            assert r == R.SZ_ERROR_UNSUPPORTED
+        else:
+            assert r == 0 and (p.lc, p.lp, p.pb) == (d % 9, (d // 9) % 5, d // 45) and p.dicSize == 4660
+            assert R.parse_lzma_props(raw) == (p.lc, p.lp, p.pb, 4660)
+    assert lib.LzmaProps_Decode(C.byref(p), bytes([0x5D, 0, 0, 0, 0]), 5) == 0 and p.dicSize == 4096
+    assert lib.LzmaProps_Decode(C.byref(p), bytes([0x5D, 0, 0, 0]), 4) == R.SZ_ERROR_UNSUPPORTED
+
+
+def test_varint_and_check_size():
+    lib = L.load()
+    lib.Xz_ReadVarInt.restype = C.c_uint
+    lib.Xz_ReadVarInt.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64)]
+    lib.XzFlags_GetCheckSize.restype = C.c_uint
+    v = C.c_uint64()
+    assert lib.Xz_ReadVarInt(bytes([0x7F]), 1, C.byref(v)) == 1 and v.value == 127
+    assert lib.Xz_ReadVarInt(bytes([0x80, 0x01]), 2, C.byref(v)) == 2 and v.value == 128
+    assert lib.Xz_ReadVarInt(bytes([0x80, 0x00]), 2, C.byref(v)) == 0          # non-minimal encoding
+    assert lib.Xz_ReadVarInt(bytes([0x80]), 1, C.byref(v)) == 0                # truncated
+    assert [lib.XzFlags_GetCheckSize(t) for t in (0, 1, 4, 10)] == [0, 4, 8, 32]
+
+
+def test_crc_tables_are_generated_like_the_reference():
+    lib = L.load()
+    lib.CrcGenerateTable()
+    lib.Crc64GenerateTable()
+    t32 = (C.c_uint32 * 2048).in_dll(lib, "g_CrcTable")
+    t64 = (C.c_uint64 * 256).in_dll(lib, "g_Crc64Table")
+    assert t32[1] == 0x77073096 and t32[255] == 0x2D02EF8D
+    assert t64[1] == 0xB32E4CBE03A75F6F
+
+
+def test_lzma2_unit_walk_matches_oracle(ora):
+    blobs, _ = cases.golden()
+    for name in ("lzma2_0", "lzma2_1", "lzma2_3", "lzma2_multi"):
+        blob = blobs[name]
+        prop = [c["prop"] for c in cases.cases_of("lzma2") if c["blob"] == name][0]
+        mine = lzb200.sdk.lzma2_index_units(blob, prop)
+        want = ora.lzma2_index(blob)
+        assert mine["res"] == 0 and mine["n"] == want["n"] and mine["has_eos"] == want["has_eos"]
+        assert mine["end_off"] == want["end_off"]
+        for u, w in zip(mine["units"], want["units"]):
+            assert (u["src_off"], u["dst_cap"]) == (w["src_off"], w["unpack_len"])
+            assert u["src_len"] == w["src_len"] and u["lc"] == w["max_lclp"] and u["codec"] == R.CODEC_LZMA2
+        assert np.array_equal(np.cumsum(mine["units"]["dst_cap"])[:-1], mine["units"]["dst_off"][1:])
+    assert lzb200.sdk.lzma2_index_units(blobs["lzma2_multi"], 41)["res"] == R.SZ_ERROR_UNSUPPORTED
+    assert lzb200.sdk.lzma2_index_units(blobs["lzma2_multi"], 20)["n"] == 4
+
+
+def test_xz_backward_index_matches_oracle(ora):
+    lib = L.load()
+    blobs, _ = cases.golden()
+
+    class Blk(C.Structure):      # include/lzb200.h: LzbXzBlock
+        _fields_ = [("hdr_off", C.c_uint64), ("hdr_size", C.c_uint32), ("data_off", C.c_uint64),
+                    ("pack_size", C.c_uint64), ("unpack_size", C.c_uint64), ("check_off", C.c_uint64),
+                    ("expect", C.c_uint64), ("filter", C.c_int32), ("filter_param", C.c_uint32),
+                    ("lzma2_prop", C.c_uint8), ("check_type", C.c_uint8), ("complete", C.c_uint8), ("pad_", C.c_uint8),
+                    ("first_unit", C.c_uint32), ("n_units", C.c_uint32)]
+    for name in ("xz0", "xz1", "xz2", "xz3"):
+        xz = blobs[name]
+        want = ora.xz_index(xz)
+        arr = (Blk * 64)()
+        n, ct = C.c_size_t(0), C.c_int(0)
+        r = lib.Xz_ReadIndexBackward(xz.ctypes.data, len(xz), arr, 64, C.byref(n), C.byref(ct))
+        assert r == want["res"] == 0 and n.value == len(want["blocks"]) and ct.value == want["check_type"]
+        for b, w in zip(arr[: n.value], want["blocks"]):
+            assert (b.hdr_off, b.hdr_size, b.data_off, b.pack_size, b.unpack_size, b.check_off) == \
+                   (w["hdr_off"], w["hdr_size"], w["data_off"], w["pack_size"], w["unpack_size"], w["check_off"])
+            assert (b.filter, b.filter_param, b.lzma2_prop) == (w["filter_id"], w["filter_param"], w["lzma2_prop"])
+        bad = xz.copy()
+        bad[-5] ^= 1
+        arr2 = (Blk * 64)()
+        assert lib.Xz_ReadIndexBackward(bad.ctypes.data, len(bad), arr2, 64, C.byref(n), C.byref(ct)) == ora.xz_index(bad)["res"] != 0

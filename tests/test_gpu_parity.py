@@ -1,0 +1,215 @@
+"""GPU parity tests proper: everything goes through the C-ABI of lib/liblzb200.so on a real B200 and is
+compared with (a) the committed golden vectors the reference produced and (b) the oracle on freshly
+seeded inputs -- bit-exact bytes and identical (SRes, status, destLen, srcLen).  At larger sizes the
+checks are size-independent properties (per-unit CRC fused on the GPU, round trips of reference-encoded
+data, digest of digests)."""
+import zlib
+
+import numpy as np
+import pytest
+
+import cases
+import lzb200
+from lzb200 import records as R
+from tools.corpus import add_x86_callsites, make_corpus
+
+pytestmark = pytest.mark.gpu
+
+
+class Gpu:
+    """refbind-shaped adapter over the product's C-ABI (lzb200.sdk)."""
+    kind = "gpu"
+
+    def lzma_decode(self, packed, props, dest_cap, finish_mode=0):
+        return lzb200.sdk.lzma_decode(packed, props, dest_cap, finish_mode)
+
+    def lzma2_decode(self, packed, prop, dest_cap, finish_mode=1):
+        return lzb200.sdk.lzma2_decode(packed, prop, dest_cap, finish_mode)
+
+    def xz_decode(self, data, dest_cap, finish_mode=0):
+        return lzb200.sdk.xz_decode(data, dest_cap)
+
+    def x86_convert(self, data, ip=0, state=0, encoding=0):
+        return lzb200.sdk.x86_convert(data, ip, state, encoding)
+
+    def delta(self, data, dist, encoding=0):
+        return lzb200.sdk.delta_decode(data, dist)[0]
+
+    def crc32(self, data):
+        return lzb200.sdk.crc32(data)
+
+    def crc64(self, data):
+        return lzb200.sdk.crc64(data)
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    return Gpu()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = lzb200.lib.Context(0)
+    yield c
+    c.close()
+
+
+def same(a, b):
+    for f in ("res", "status", "dest_len", "src_len"):
+        assert a[f] == b[f], (f, {k: a[k] for k in a if k != "out"}, {k: b[k] for k in b if k != "out"})
+    assert np.array_equal(a["out"][: a["dest_len"]], b["out"][: b["dest_len"]])
+
+
+# ------------------------------------------------------------------ golden vectors (reference-made)
+@pytest.mark.parametrize("kind", ["lzma", "lzma2"])
+def test_golden_decodes(gpu, kind):
+    blobs, _ = cases.golden()
+    for c in cases.cases_of(kind):
+        cases.check_decode_case(gpu, c, blobs)
+
+
+def test_golden_xz(gpu):
+    blobs, _ = cases.golden()
+    for c in cases.cases_of("xz"):
+        cases.check_xz_case(gpu, c, blobs)
+
+
+@pytest.mark.parametrize("kind", ["x86", "delta", "crc"])
+def test_golden_filters_and_checks(gpu, kind):
+    blobs, _ = cases.golden()
+    for c in cases.cases_of(kind):
+        cases.check_filter_case(gpu, c, blobs)
+
+
+# ------------------------------------------------------------------ fresh inputs vs the oracle
+def test_lzma_fuzz_against_oracle(gpu, ora):
+    """bit flips / truncations / odd capacities on golden streams, compared with the oracle."""
+    blobs, _ = cases.golden()
+    rng = np.random.default_rng(77)
+    seen = set()
+    for c in [x for x in cases.cases_of("lzma") if x["mut"] is None and x["finish"] == 0 and x["cap"] > 0][:9]:
+        packed, props, n = blobs[c["blob"]], bytes.fromhex(c["props"]), c["cap"]
+        for _ in range(12):
+            bad = packed.copy()
+            if len(bad) > 8:
+                bad[int(rng.integers(0, len(bad)))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            cut = int(rng.integers(0, len(bad) + 1)) if rng.integers(0, 3) == 0 else len(bad)
+            cap = int(rng.integers(0, n + 50)) if rng.integers(0, 3) == 0 else n
+            fm = int(rng.integers(0, 2))
+            a, b = ora.lzma_decode(bad[:cut], props, cap, fm), gpu.lzma_decode(bad[:cut], props, cap, fm)
+            same(a, b)
+            seen.add(a["res"])
+    assert {0, 1, 6} <= seen
+
+
+def test_batch_matches_per_stream_calls(gpu, ora, ctx):
+    """LzmaUncompressBatch == n LzmaUncompress calls, including bad members that must not poison neighbours."""
+    blobs, _ = cases.golden()
+    good = [x for x in cases.cases_of("lzma") if x["mut"] is None and x["finish"] == 0]
+    packed_list, caps, props = [], [], []
+    rng = np.random.default_rng(5)
+    for i in range(300):
+        c = good[i % len(good)]
+        p = blobs[c["blob"]]
+        if i % 17 == 3 and len(p) > 30:
+            p = p.copy()
+            p[int(rng.integers(5, len(p)))] ^= 0x40
+        if i % 29 == 7:
+            p = p[: len(p) // 2]
+        packed_list.append(p)
+        caps.append(c["cap"])
+        props.append(bytes.fromhex(c["props"]))
+    out = lzb200.sdk.lzma_uncompress_batch(ctx, packed_list, b"".join(props), caps)
+    for i, d in enumerate(out):
+        want = ora.lzma_decode(packed_list[i], props[i], caps[i], 0)
+        assert (d["res"], d["dest_len"], d["src_len"]) == (want["res"], want["dest_len"], want["src_len"]), i
+        assert np.array_equal(d["out"][: d["dest_len"]], want["out"][: want["dest_len"]]), i
+
+
+def test_many_units_digest_of_digests(ctx, ora):
+    """4096 raw LZMA units through Lzb_DecodeUnitsHost with the CRC-32 fused on the GPU: every unit must verify
+    against the digest of its plain text, and the XOR of all GPU digests equals the host's."""
+    blobs, _ = cases.golden()
+    src = [x for x in cases.cases_of("lzma") if x["mut"] is None and x["finish"] == 0 and x["cap"] >= 5000
+           and x["props"] == "5d00000100"]
+    assert src
+    n = 4096
+    lens = np.array([len(blobs[src[i % len(src)]["blob"]]) for i in range(n)], dtype=np.uint32)
+    caps = np.array([src[i % len(src)]["cap"] for i in range(n)], dtype=np.uint32)
+    soff = np.concatenate(([0], np.cumsum((lens.astype(np.uint64) + 3) & ~np.uint64(3))[:-1])).astype(np.uint64)
+    doff = np.concatenate(([0], np.cumsum(caps.astype(np.uint64))[:-1])).astype(np.uint64)
+    packed = lzb200.sdk.pinned_empty(int(soff[-1] + lens[-1] + 16))
+    for i in range(n):
+        packed[int(soff[i]):int(soff[i]) + int(lens[i])] = blobs[src[i % len(src)]["blob"]]
+    out = lzb200.sdk.pinned_empty(int(doff[-1] + caps[-1]))
+    units = lzb200.sdk.raw_lzma_units(soff, lens, doff, caps, bytes.fromhex("5d00000100"))
+    units["check"], units["flags"] = R.CHECK_CRC32, R.UNIT_VERIFY
+    units["expect"] = [src[i % len(src)]["plain_crc"] for i in range(n)]
+    res = lzb200.sdk.decode_units_host(ctx, packed, out, units)
+    assert (res["res"] == 0).all(), np.unique(res["res"], return_counts=True)
+    assert (res["dst_done"] == caps).all() and (res["src_used"] == lens).all()
+    assert np.bitwise_xor.reduce(res["check"]) == np.bitwise_xor.reduce(units["expect"])
+    k = 1234
+    assert zlib.crc32(out[int(doff[k]):int(doff[k]) + int(caps[k])].tobytes()) == src[k % len(src)]["plain_crc"]
+    lzb200.sdk.pinned_free_all()
+
+
+def test_lzma2_parallel_units_and_limits(gpu, ora):
+    blobs, _ = cases.golden()
+    blob = blobs["lzma2_multi"]
+    prop = [c["prop"] for c in cases.cases_of("lzma2") if c["blob"] == "lzma2_multi"][0]
+    total = 360000
+    rng = np.random.default_rng(9)
+    for cap in (total, total + 1, total - 1, 90000, 89999, 90001, 180000, 1, 0):
+        for fm in (0, 1):
+            same(ora.lzma2_decode(blob, prop, cap, fm), gpu.lzma2_decode(blob, prop, cap, fm))
+    for _ in range(25):
+        bad = blob.copy()
+        bad[int(rng.integers(0, len(bad)))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        cut = int(rng.integers(0, len(bad) + 1)) if rng.integers(0, 4) == 0 else len(bad)
+        for fm in (0, 1):
+            same(ora.lzma2_decode(bad[:cut], prop, total, fm), gpu.lzma2_decode(bad[:cut], prop, total, fm))
+
+
+@pytest.mark.needref
+def test_fresh_reference_encoded_round_trips(gpu, ref, ora):
+    """new data, encoded by the reference encoder here, decoded on the GPU: LZMA, LZMA2 and xz."""
+    corpus = add_x86_callsites(make_corpus(3 << 20, seed=4242), seed=4)
+    packed, props = ref.lzma_encode(corpus[:200000], level=5, dict_size=1 << 16)
+    d = gpu.lzma_decode(packed, props, 200000, 0)
+    assert d["res"] == 0 and np.array_equal(d["out"], corpus[:200000])
+    parts, prop = [], 0
+    for k in range(3):
+        pk, prop = ref.lzma2_encode(corpus[k << 20:(k + 1) << 20], level=1, dict_size=1 << 20)
+        parts.append(pk if k == 2 else pk[:-1])
+    d = gpu.lzma2_decode(np.concatenate(parts), prop, 3 << 20, 1)
+    assert (d["res"], d["status"], d["dest_len"]) == (0, 1, 3 << 20) and np.array_equal(d["out"], corpus)
+    # xz: 4 MiB-class blocks would take long on the slow reference encoder; 512 KiB blocks, BCJ + CRC64
+    pk_list, lens, ulen, checks = [], [], [], []
+    for b0 in range(0, 2 << 20, 1 << 19):
+        blk = corpus[b0:b0 + (1 << 19)]
+        pk, prop = ref.lzma2_encode(ref.x86_filter_whole(blk, 0, 1), level=1, dict_size=1 << 20)
+        pk_list.append(pk); lens.append(len(pk)); ulen.append(len(blk)); checks.append(ref.crc64(blk))
+    offs = np.concatenate(([0], np.cumsum(lens)[:-1]))
+    xz = ref.xz_assemble(np.concatenate(pk_list), offs, lens, ulen, checks, 4, 4, 0, prop)
+    a, b = ref.xz_decode(xz, (2 << 20) + 8), gpu.xz_decode(xz, (2 << 20) + 8)
+    assert (b["res"], b["status"], b["dest_len"], b["src_len"], b["num_blocks"], b["finished"]) == \
+           (a["res"], a["status"], a["dest_len"], a["src_len"], a["num_blocks"], a["finished"])
+    assert np.array_equal(b["out"][: 2 << 20], corpus[: 2 << 20])
+
+
+def test_filters_and_checks_large(gpu, ora):
+    data = add_x86_callsites(make_corpus(3_000_001, seed=11), seed=12, every=31)
+    assert gpu.crc32(data) == ora.crc32(data) == zlib.crc32(data.tobytes())
+    assert gpu.crc64(data) == ora.crc64(data)
+    assert lzb200.sdk.crc32_update(0x1234, data[:70001]) == (zlib.crc32(data[:70001].tobytes(), 0x1234 ^ 0xFFFFFFFF) ^ 0xFFFFFFFF)
+    for enc in (0, 1):
+        a, b = ora.x86_convert(data, 0, 0, enc), gpu.x86_convert(data, 0, 0, enc)
+        assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+    for dist in (1, 2, 3, 4, 33, 256):
+        assert np.array_equal(ora.delta(data, dist, 0), gpu.delta(data, dist))
+    # carried history across two Delta_Decode calls == one call
+    one = ora.delta(data[:100000], 5, 0)
+    first, st = lzb200.sdk.delta_decode(data[:40001], 5)
+    second, _ = lzb200.sdk.delta_decode(data[40001:100000], 5, st)
+    assert np.array_equal(np.concatenate((first, second)), one)

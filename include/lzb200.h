@@ -213,8 +213,8 @@ void Lzb_HostFree(void *p);
 SRes Lzb_DecodeUnitsHost(LzbContext *ctx, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
                          const LzbUnit *units, LzbResult *results, size_t n);
 
-/* Same with both arenas already resident in DEVICE memory; asynchronous on `stream` (a cudaStream_t,
- * 0 = the context's own stream).  d_units / d_results are device arrays.  The packed arena must be
+/* Same with both arenas already resident in DEVICE memory; asynchronous on `stream` (a cudaStream_t;
+ * NULL = the CUDA default stream).  d_units / d_results are device arrays.  The packed arena must be
  * readable up to the next 4-byte boundary past its last unit. */
 SRes Lzb_DecodeUnitsDevice(LzbContext *ctx, const Byte *d_packed, Byte *d_out, const LzbUnit *d_units,
                            LzbResult *d_results, size_t n, unsigned maxLcLp, unsigned maxPb, void *stream);

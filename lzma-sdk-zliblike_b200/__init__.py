@@ -18,7 +18,7 @@ __all__ = ["records", "build", "lib", "sdk", "batch"]
 
 
 def __getattr__(name):
-    if name in ("lib", "sdk", "batch", "buildlib"):
+    if name in ("lib", "sdk", "sharding", "buildlib"):
         return importlib.import_module(f"{__name__}.{name}")
     if name == "build":
         return importlib.import_module(f"{__name__}.buildlib").build

@@ -205,19 +205,22 @@ struct UnitDecoder
   /* LzmaDec.c:19-21 */
   LZB_FN uint32_t rc_bit(uint16_t *p)
   {
+    /* select form (no branch on the decoded bit): every lane takes the same straight-line path.
+     * Probability update, both outcomes in one expression:
+     *   bit 0:  p + ((2048 - p) >> 5)  ==  p - ((p - 2017) >>arith 5)      (floor division of a negative)
+     *   bit 1:  p - (p >> 5)           ==  p - ((p -    0) >>arith 5)                                   */
     const uint32_t pr = *p;
     rc_norm();
     const uint32_t bound = (range >> 11) * pr;
-    if (code < bound)
-    {
-      range = bound;
-      *p = (uint16_t)(pr + ((2048u - pr) >> 5));
-      return 0;
-    }
-    range -= bound;
-    code -= bound;
-    *p = (uint16_t)(pr - (pr >> 5));
-    return 1;
+    const bool one = code >= bound;
+    const uint32_t rest = range - bound;
+    range = one ? rest : bound;
+    code = one ? code - bound : code;
+    /* (2048 - p) >> 5 == 64 - ((p + 31) >> 5), so with (A, B) = bit ? (0, 0) : (64, 31):
+     *   p' = p + A - ((p + B) >> 5)   -- unsigned throughout, one select feeds both constants */
+    const uint32_t ab = one ? 0u : ((64u << 16) | 31u);
+    *p = (uint16_t)(pr + (ab >> 16) - ((pr + (ab & 0xFFFFu)) >> 5));
+    return one ? 1u : 0u;
   }
 
   /* LzmaDec.c:325-334, exact wrap-around arithmetic */

@@ -57,6 +57,7 @@ extern "C" LzbContext *Lzb_Create(int device)
       return nullptr;
     }
   }
+  if (!lzb_cuda_ok(cudaMalloc(&c->d_dev_tickets, 64 * sizeof(uint32_t)), "cudaMalloc tickets")) { Lzb_Destroy(c); return nullptr; }
   return c;
 }
 
@@ -73,6 +74,7 @@ extern "C" void Lzb_Destroy(LzbContext *c)
     if (s.h_units) cudaFreeHost(s.h_units);
     if (s.h_results) cudaFreeHost(s.h_results);
   }
+  cudaFree(c->d_dev_tickets); cudaFree(c->d_dev_slab);
   delete c;
 }
 
@@ -168,12 +170,12 @@ extern "C" SRes Lzb_DecodeUnitsDevice(LzbContext *c, const Byte *d_packed, Byte 
   if (n > 0xFFFFFFFFull) return SZ_ERROR_PARAM;
   std::lock_guard<std::mutex> g(c->mu);
   if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
-  LzbSlot &s = c->slot[0];
   const uint32_t model = lzb_num_probs(maxLcLp, 0, maxPb) * 2u;
   const size_t slab = slab_bytes_for(model);
-  if (slab && !grow(s.d_slab, s.slab_cap, slab, "cudaMalloc model slab")) return SZ_ERROR_MEM;
-  cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
-  int rc = lzb_launch_decode(d_packed, d_out, d_units, d_results, (uint32_t)n, s.d_ticket, model, s.d_slab, st);
+  if (slab && !grow(c->d_dev_slab, c->dev_slab_cap, slab, "cudaMalloc model slab")) return SZ_ERROR_MEM;
+  cudaStream_t st = (cudaStream_t)stream;        /* NULL = the CUDA default stream, as everywhere in CUDA */
+  uint32_t *ticket = c->d_dev_tickets + (c->dev_seq++ % 64);
+  int rc = lzb_launch_decode(d_packed, d_out, d_units, d_results, (uint32_t)n, ticket, model, c->d_dev_slab, st);
   if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
   return SZ_OK;
 }

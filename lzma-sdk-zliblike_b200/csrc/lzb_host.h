@@ -30,6 +30,10 @@ struct LzbContext
   int device = 0;
   int sms = 0;
   LzbSlot slot[LZB_SLOTS];
+  /* device-resident API: its own ticket ring (one counter per launch in flight) and model slab */
+  uint32_t *d_dev_tickets = nullptr;
+  unsigned dev_seq = 0;
+  uint8_t *d_dev_slab = nullptr; size_t dev_slab_cap = 0;
   std::mutex mu;
 };
 

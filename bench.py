@@ -383,7 +383,9 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(a.workload)
+            rec = json.load(open(tp)).get(a.workload)
+            if rec:   # measured DRAM bytes per algorithmic byte (ncu --set full), scaled to this launch
+                traffic = int(rec["dram_bytes_per_algorithmic_byte"] * (t["sum_p"] + t["sum_u"]))
         except Exception:
             traffic = None
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,

@@ -148,7 +148,8 @@ def test_many_units_digest_of_digests(ctx, ora):
     res = lzb200.sdk.decode_units_host(ctx, packed, out, units)
     assert (res["res"] == 0).all(), np.unique(res["res"], return_counts=True)
     want_src = np.array([src[i % len(src)]["src_len"] for i in range(n)], dtype=np.uint32)   # excludes an end mark
-    assert (res["dst_done"] == caps).all() and (res["src_used"] == want_src).all()
+    want_dst = np.array([src[i % len(src)]["dest_len"] for i in range(n)], dtype=np.uint32)  # < cap when a mark ends it
+    assert (res["dst_done"] == want_dst).all() and (res["src_used"] == want_src).all()
     assert np.bitwise_xor.reduce(res["check"]) == np.bitwise_xor.reduce(units["expect"])
     k = 1234
     assert zlib.crc32(out[int(doff[k]):int(doff[k]) + int(caps[k])].tobytes()) == src[k % len(src)]["plain_crc"]

@@ -163,6 +163,7 @@ struct UnitDecoder
   uint32_t prev_byte;      /* dic[dicPos-1] (0 right after a dictionary reset)          */
   uint32_t peek_byte;      /* dic[dicPos-rep0], valid while state >= 7 (matched literal) */
   bool want_rc_init, want_state_init;
+  uint32_t held_out;       /* input bytes parked for the next call (CLzmaDec.tempBufSize) when starved */
 
   /* ---------------- input window ---------------- */
   LZB_FN uint32_t in_pos() const { return fetch - win_left; }
@@ -642,6 +643,8 @@ struct UnitDecoder
   {
     bool ctx_stale = false;
     used = 0;
+    held_out = 0;
+    if (!want_rc_init) { rc_seek(src); ctx_stale = true; }     /* continuing a chunk / a suspended stream */
     flush_pending(dic_limit);
     status = LZB_ST_NOT_SPECIFIED;
     while (pending != kEndMarkLen)
@@ -649,7 +652,7 @@ struct UnitDecoder
       bool must_end = false;
       if (want_rc_init)                                                          /* :732-746 */
       {
-        if (avail < 5) { used += avail; status = LZB_ST_NEEDS_MORE_INPUT; return LZB_SZ_OK; }
+        if (avail < 5) { used += avail; held_out = avail; status = LZB_ST_NEEDS_MORE_INPUT; return LZB_SZ_OK; }
         used += 5;
         if (in[src] != 0) return LZB_SZ_ERROR_DATA;
         code = ((uint32_t)in[src + 1] << 24) | ((uint32_t)in[src + 2] << 16) | ((uint32_t)in[src + 3] << 8) | in[src + 4];
@@ -673,7 +676,7 @@ struct UnitDecoder
       if (avail < kLookahead || must_end)                                        /* :776-793 */
       {
         const int k = peek_symbol(src, avail);
-        if (k == kSymStarved) { used += avail; status = LZB_ST_NEEDS_MORE_INPUT; return LZB_SZ_OK; }
+        if (k == kSymStarved) { used += avail; held_out = avail; status = LZB_ST_NEEDS_MORE_INPUT; return LZB_SZ_OK; }
         if (must_end && k != kSymMatch) { status = LZB_ST_NOT_FINISHED; return LZB_SZ_ERROR_DATA; }
         soft_end = src;
       }
@@ -692,9 +695,51 @@ struct UnitDecoder
     lc = lc_; lp = lp_; lp_mask = (1u << lp_) - 1; pb = pb_; pb_mask = (1u << pb_) - 1;
   }
 
+  /* resumable decoders: scalars <-> LzbStreamState, model <-> the words behind its header */
+  LZB_FN void load_state(const LzbStreamState *s)
+  {
+    range = s->range; code = s->code; state = s->state;
+    rep0 = s->rep[0]; rep1 = s->rep[1]; rep2 = s->rep[2]; rep3 = s->rep[3];
+    total_pos = s->total_pos; dict_full = s->dict_full; pending = s->pending;
+    want_rc_init = (s->flags & 1) != 0; want_state_init = (s->flags & 2) != 0;
+    dic_pos = dic_commit = s->dic_pos;
+    set_props(s->lc, s->lp, s->pb);
+    if (!want_state_init)
+    {
+      const uint32_t n32 = lzb_num_probs(lc, lp, pb) >> 1;
+      const uint32_t *g = reinterpret_cast<const uint32_t *>(s + 1);
+      uint32_t *p32 = reinterpret_cast<uint32_t *>(probs);
+      for (uint32_t i = lzb_lane(); i < n32; i += LZB_LANES) p32[i] = g[i];
+      lzb_syncwarp();
+    }
+  }
+
+  LZB_FN void save_state(LzbStreamState *s) const
+  {
+    lzb_syncwarp();
+    if (!want_state_init)
+    {
+      const uint32_t n32 = lzb_num_probs(lc, lp, pb) >> 1;
+      uint32_t *g = reinterpret_cast<uint32_t *>(s + 1);
+      const uint32_t *p32 = reinterpret_cast<const uint32_t *>(probs);
+      for (uint32_t i = lzb_lane(); i < n32; i += LZB_LANES) g[i] = p32[i];
+    }
+    if (lzb_lane() == 0)
+    {
+      s->range = range; s->code = code; s->state = state;
+      s->rep[0] = rep0; s->rep[1] = rep1; s->rep[2] = rep2; s->rep[3] = rep3;
+      s->total_pos = total_pos; s->dict_full = dict_full; s->pending = pending;
+      s->flags = (want_rc_init ? 1u : 0u) | (want_state_init ? 2u : 0u);
+      s->dic_pos = dic_commit;
+      s->held = held_out;
+      s->lc = lc; s->lp = lp; s->pb = pb;
+    }
+  }
+
   LZB_FN void begin(const uint8_t *packed, uint32_t packed_len, uint8_t *out, uint32_t out_cap,
                     uint32_t dict, uint16_t *model)
   {
+    held_out = 0;
     in = packed; in_len = packed_len;
     in_skew = (uint32_t)((uintptr_t)packed & 3);
     wbase = reinterpret_cast<const uint32_t *>(packed - in_skew);
@@ -718,8 +763,9 @@ struct UnitDecoder
  * header machine (:98-157) folded into the loop.  The unit's chunk headers are re-read here by
  * the decoding warp (<= 6 bytes per <= 2 MiB chunk); the HOST walks the same headers once to cut
  * the stream into units (dictionary-reset groups) -- see lzb_host.cu. */
-LZB_FN void decode_unit(UnitDecoder &d, const LzbUnit &u, LzbResult &r)
+LZB_FN void decode_unit(UnitDecoder &d, const LzbUnit &u, LzbResult &r, LzbStreamState *st = nullptr)
 {
+  /* phase numbering == ELzma2State (Lzma2Dec.c:47-59): it is what CLzma2Dec.state holds between calls */
   enum { PH_CONTROL, PH_U0, PH_U1, PH_P0, PH_P1, PH_PROPS, PH_DATA, PH_DATA_MORE, PH_FINISHED, PH_ERROR };
   const uint8_t *in = d.in;
   const uint32_t in_size = u.src_len, dic_limit = u.dst_cap;
@@ -732,12 +778,24 @@ LZB_FN void decode_unit(UnitDecoder &d, const LzbUnit &u, LzbResult &r)
   r.check = 0;
   if (raw)
   {
-    if (in_size < 5) { r.res = LZB_SZ_ERROR_INPUT_EOF; r.status = status; r.src_used = 0; r.dst_done = 0; return; }
+    if (!st && in_size < 5) { r.res = LZB_SZ_ERROR_INPUT_EOF; r.status = status; r.src_used = 0; r.dst_done = 0; return; }
     d.set_props(u.lc, u.lp, u.pb);
     control = 0x80; phase = PH_DATA_MORE; pack_left = in_size; unpack_left = 0xFFFFFFFFu;
   }
   else
     d.set_props(4, 0, 0);                              /* Lzma2Dec_GetOldProps, Lzma2Dec.c:61-73 */
+  if (st)
+  {
+    /* resume: CLzmaDec / CLzma2Dec as the previous call left them (host keeps the scalars authoritative) */
+    d.load_state(st);
+    if (!raw)
+    {
+      phase = (int)st->l2_phase; control = st->l2_control;
+      pack_left = st->l2_pack_left + st->held;         /* bytes parked in tempBuf were already charged */
+      unpack_left = st->l2_unpack_left;
+      want_dic = (st->l2_flags & 1) != 0; want_state = (st->l2_flags & 2) != 0; want_props = (st->l2_flags & 4) != 0;
+    }
+  }
 
   for (;;)
   {
@@ -827,7 +885,7 @@ LZB_FN void decode_unit(UnitDecoder &d, const LzbUnit &u, LzbResult &r)
       if (raw)
       {
         /* one-call LzmaDecode (LzmaDec.c:972-1002), which LzmaUncompress wraps with FINISH_ANY */
-        if (res == LZB_SZ_OK && status == LZB_ST_NEEDS_MORE_INPUT) res = LZB_SZ_ERROR_INPUT_EOF;
+        if (!st && res == LZB_SZ_OK && status == LZB_ST_NEEDS_MORE_INPUT) res = LZB_SZ_ERROR_INPUT_EOF;
         break;
       }
       pack_left -= used;
@@ -845,6 +903,16 @@ LZB_FN void decode_unit(UnitDecoder &d, const LzbUnit &u, LzbResult &r)
     }
   }
   r.res = res; r.status = status; r.src_used = at_in; r.dst_done = d.dic_commit; r.check = 0;
+  if (st)
+  {
+    d.save_state(st);
+    if (lzb_lane() == 0)
+    {
+      st->l2_phase = (uint32_t)phase; st->l2_control = control;
+      st->l2_pack_left = pack_left; st->l2_unpack_left = unpack_left;
+      st->l2_flags = (want_dic ? 1u : 0u) | (want_state ? 2u : 0u) | (want_props ? 4u : 0u);
+    }
+  }
 }
 
 }  // namespace lzb

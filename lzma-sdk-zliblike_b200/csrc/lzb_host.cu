@@ -281,6 +281,23 @@ extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t pa
   return ret;
 }
 
+/* Run a few units whose arenas the caller already placed in device memory; unit table and results are
+ * host arrays.  Synchronous.  Used by the stateful SDK objects (lzb_state.cu). */
+SRes lzb_run_resident(LzbContext *c, const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *units, LzbResult *results, size_t n)
+{
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
+  LzbSlot &s = c->slot[0];
+  const uint32_t model = model_bytes_for(units, n);
+  if (!lzb_slot_reserve(c, s, 0, 0, n, slab_bytes_for(model))) return SZ_ERROR_MEM;
+  if (!lzb_cuda_ok(cudaMemcpyAsync(s.d_units, units, n * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D units")) return SZ_ERROR_FAIL;
+  int rc = lzb_launch_decode(d_packed, d_out, s.d_units, s.d_results, (uint32_t)n, s.d_ticket, model, s.d_slab, s.stream);
+  if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+  if (!lzb_cuda_ok(cudaMemcpyAsync(results, s.d_results, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results") ||
+      !lzb_cuda_ok(cudaStreamSynchronize(s.stream), "decode kernel")) return SZ_ERROR_FAIL;
+  return SZ_OK;
+}
+
 SRes lzb_decode_host_simple(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
                             const LzbUnit *units, LzbResult *results, size_t n)
 {

@@ -46,6 +46,8 @@ bool lzb_slot_reserve(LzbContext *c, LzbSlot &s, size_t packed, size_t out, size
 SRes lzb_decode_host_simple(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
                             const LzbUnit *units, LzbResult *results, size_t n);
 
+SRes lzb_run_resident(LzbContext *c, const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *units, LzbResult *results, size_t n);
+
 /* little helpers */
 static inline uint32_t lzb_le32(const Byte *p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 static inline uint64_t lzb_le64(const Byte *p) { return (uint64_t)lzb_le32(p) | ((uint64_t)lzb_le32(p + 4) << 32); }

@@ -39,9 +39,11 @@ lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict_
     UnitDecoder d;
     LzbResult r;
     uint8_t *dst = out + u.dst_off;
-    d.begin(packed + u.src_off, u.src_len, dst, u.dst_cap, u.dict_size, reinterpret_cast<uint16_t *>(region));
-    decode_unit(d, u, r);
-    post_process(u, r, dst, region);
+    const bool stateful = (u.flags & LZB_UNIT_STATEFUL) != 0;
+    d.begin(packed + u.src_off, u.src_len, dst, stateful ? u.filter_param : u.dst_cap, u.dict_size,
+            reinterpret_cast<uint16_t *>(region));
+    decode_unit(d, u, r, stateful ? reinterpret_cast<LzbStreamState *>(u.expect) : nullptr);
+    if (!stateful) post_process(u, r, dst, region);
     if (lane == 0) results[i] = r;
     __syncwarp();
   }

@@ -1,15 +1,21 @@
-/* lzb_state.cu -- the SDK's stateful interfaces (dictionary / buffer interface of LzmaDec.h and the
- * Lzma2Dec.h state interface) on top of the GPU path.
+/* lzb_state.cu -- the SDK's stateful interfaces on the GPU path: the dictionary / buffer interfaces of
+ * LzmaDec.h (LzmaDec_DecodeToDic, LzmaDec_DecodeToBuf) and the state interface of Lzma2Dec.h.
  *
- * CLzmaDec.probs does not hold probabilities here (they live in device memory); it points at a small
- * host control block obtained from the caller's ISzAlloc, so Allocate/Free pair up as in the reference.
+ * A decoder object is resumable exactly like the reference's: any call may stop at any input or
+ * output byte (NEEDS_MORE_INPUT, output limit) and the next call continues.  Division of labour:
  *
- * Round-1 behaviour: a decoder object decodes ONE whole buffer per LzmaDec_Init / Lzma2Dec_Init -- the
- * pattern of LzmaDecode (LzmaDec.c:984-999) and of 7zDec.c:134-152,184-202 when the folder's packed
- * bytes are handed over in one piece.  A call that would have to RESUME a suspended stream (partial
- * input fed in pieces, LzmaUtil.c:55-106) returns SZ_ERROR_UNSUPPORTED with an explanatory
- * Lzb_LastError(); it never falls back to a CPU decoder.  Suspend/resume of device-resident state is
- * the next item of SURVEY.md §8f.
+ *   host   CLzmaDec / CLzma2Dec keep every scalar field of the reference with the reference's meaning
+ *          (range, code, dicPos, processedPos, checkDicSize, state, reps, remainLen, needFlush,
+ *          needInitState, tempBuf/tempBufSize; packSize, unpackSize, state, control, needInit*) -- the
+ *          caller may read and poke them as it does with the reference (7zDec.c:135-157).
+ *   device the probability model and a mirror of the dictionary live in device memory between calls
+ *          (CLzmaDec.probs points at a small host control block that owns them).
+ *
+ * Each call uploads the scalars + the new input, runs ONE stateful unit (csrc/lzb_core.cuh, flag
+ * LZB_UNIT_STATEFUL) and downloads scalars + the newly produced dictionary range.  Instead of the
+ * reference's tempBuf branch (LzmaDec.c:804-833) the bytes parked in tempBuf are re-presented in front
+ * of the new input, which decodes the same symbols.  A single stream still runs on a single warp: this
+ * interface exists for drop-in completeness, the throughput is in the batched calls.
  */
 #include "lzb_host.h"
 
@@ -19,12 +25,21 @@
 struct LzbCtl
 {
   uint64_t magic;
-  int owns_dic;
-  int used;            /* a whole-buffer decode has consumed this Init */
+  uint8_t *d_state; size_t state_bytes;
+  uint8_t *d_dic;   size_t dic_cap;
+  uint8_t *d_in;    size_t in_cap;
 };
-#define LZB_CTL_MAGIC 0x4C5A4243544C3031ull
+#define LZB_CTL_MAGIC 0x4C5A4243544C3032ull
 
 static LzbCtl *ctl_of(CLzmaDec *p) { return (LzbCtl *)(void *)p->probs; }
+
+static void ctl_release_device(LzbCtl *c)
+{
+  if (!c || c->magic != LZB_CTL_MAGIC) return;
+  cudaFree(c->d_state); cudaFree(c->d_dic); cudaFree(c->d_in);
+  c->d_state = c->d_dic = c->d_in = nullptr;
+  c->state_bytes = c->dic_cap = c->in_cap = 0;
+}
 
 static SRes alloc_ctl(CLzmaDec *p, const CLzmaProps *pr, ISzAlloc *alloc)
 {
@@ -45,6 +60,7 @@ static SRes alloc_ctl(CLzmaDec *p, const CLzmaProps *pr, ISzAlloc *alloc)
 
 extern "C" void LzmaDec_FreeProbs(CLzmaDec *p, ISzAlloc *alloc)
 {
+  if (p->probs) ctl_release_device(ctl_of(p));
   alloc->Free(alloc, p->probs);
   p->probs = 0;
 }
@@ -101,83 +117,148 @@ extern "C" void LzmaDec_Init(CLzmaDec *p)
 {
   p->dicPos = 0;
   LzmaDec_InitDicAndState(p, 1, 1);
-  if (p->probs && ctl_of(p)->magic == LZB_CTL_MAGIC) ctl_of(p)->used = 0;
 }
 
-static SRes need_fresh(CLzmaDec *p, const char *who)
+template <class T> static bool grow_dev(T *&ptr, size_t &cap, size_t need, const char *what)
 {
+  if (need <= cap && ptr) return true;
+  cudaFree(ptr);
+  ptr = nullptr; cap = 0;
+  if (!lzb_cuda_ok(cudaMalloc((void **)&ptr, need + 64), what)) return false;
+  cap = need;
+  return true;
+}
+
+/* One stateful step.  l2 == NULL: raw LZMA (LzmaDec_DecodeToDic); else the LZMA2 layer as well. */
+static SRes step(CLzmaDec *p, CLzma2Dec *l2, SizeT dicLimit, const Byte *src, SizeT *srcLen,
+                 ELzmaFinishMode finishMode, ELzmaStatus *status, const char *who)
+{
+  const SizeT inSize = *srcLen;
+  *srcLen = 0;
+  *status = LZMA_STATUS_NOT_SPECIFIED;
   if (!p->probs || ctl_of(p)->magic != LZB_CTL_MAGIC) { lzb_set_error("%s: decoder not allocated", who); return SZ_ERROR_PARAM; }
-  if (ctl_of(p)->used || !p->needFlush || p->processedPos != 0 || p->dicPos != 0)
+  if (!p->dic || dicLimit > p->dicBufSize) { lzb_set_error("%s: dicLimit beyond dicBufSize", who); return SZ_ERROR_PARAM; }
+  if (p->dicBufSize > 0xFFFFFFFFull || inSize > 0xFFFFFF00ull) { lzb_set_error("%s: buffers above 4 GiB", who); return SZ_ERROR_UNSUPPORTED; }
+  LzbContext *c = lzb_default_context();
+  if (!c) return SZ_ERROR_FAIL;
+  if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
+  LzbCtl *ctl = ctl_of(p);
+
+  const unsigned mlc = l2 ? 4 : p->prop.lc, mlp = l2 ? 0 : p->prop.lp, mpb = l2 ? 4 : p->prop.pb;
+  const size_t state_bytes = sizeof(LzbStreamState) + (size_t)lzb_num_probs(mlc, mlp, mpb) * 2;
+  const unsigned prefix = p->tempBufSize;
+  const size_t total_in = (size_t)prefix + inSize;
+  if (!grow_dev(ctl->d_state, ctl->state_bytes, state_bytes, "cudaMalloc decoder state") ||
+      !grow_dev(ctl->d_dic, ctl->dic_cap, p->dicBufSize, "cudaMalloc dictionary mirror") ||
+      !grow_dev(ctl->d_in, ctl->in_cap, total_in + 16, "cudaMalloc input staging"))
+    return SZ_ERROR_MEM;
+
+  LzbStreamState st;
+  memset(&st, 0, sizeof st);
+  st.range = p->range; st.code = p->code; st.state = p->state;
+  for (int i = 0; i < 4; i++) st.rep[i] = p->reps[i];
+  st.total_pos = p->processedPos; st.dict_full = p->checkDicSize; st.pending = p->remainLen;
+  st.flags = (p->needFlush ? 1u : 0u) | (p->needInitState ? 2u : 0u);
+  st.dic_pos = (uint32_t)p->dicPos;
+  st.held = prefix;
+  st.lc = p->prop.lc; st.lp = p->prop.lp; st.pb = p->prop.pb;
+  if (l2)
   {
-    lzb_set_error("%s: resuming a suspended stream is not supported in this round; call the Init function and "
-                  "present the whole packed buffer in one call", who);
-    return SZ_ERROR_UNSUPPORTED;
+    st.l2_phase = (uint32_t)l2->state; st.l2_control = l2->control;
+    st.l2_pack_left = l2->packSize; st.l2_unpack_left = l2->unpackSize;
+    st.l2_flags = (l2->needInitDic ? 1u : 0u) | (l2->needInitState ? 2u : 0u) | (l2->needInitProp ? 4u : 0u);
   }
-  return SZ_OK;
+  bool ok = lzb_cuda_ok(cudaMemcpy(ctl->d_state, &st, sizeof st, cudaMemcpyHostToDevice), "H2D state");
+  if (ok && prefix) ok = lzb_cuda_ok(cudaMemcpy(ctl->d_in, p->tempBuf, prefix, cudaMemcpyHostToDevice), "H2D held bytes");
+  if (ok && inSize) ok = lzb_cuda_ok(cudaMemcpy(ctl->d_in + prefix, src, inSize, cudaMemcpyHostToDevice), "H2D input");
+  if (!ok) return SZ_ERROR_FAIL;
+
+  LzbUnit u;
+  LzbResult x;
+  memset(&u, 0, sizeof u);
+  u.src_len = (uint32_t)total_in; u.dst_cap = (uint32_t)dicLimit; u.dict_size = p->prop.dicSize;
+  u.codec = l2 ? LZB_CODEC_LZMA2 : LZB_CODEC_LZMA;
+  u.lc = (uint8_t)mlc; u.lp = (uint8_t)mlp; u.pb = (uint8_t)mpb;      /* model sizing (LZMA2: worst case) */
+  u.finish = (uint8_t)finishMode;
+  u.flags = LZB_UNIT_STATEFUL;
+  u.filter_param = (uint32_t)p->dicBufSize;
+  u.expect = (uint64_t)(uintptr_t)ctl->d_state;
+  SRes r = lzb_run_resident(c, ctl->d_in, ctl->d_dic, &u, &x, 1);
+  if (r != SZ_OK) return r;
+  const SizeT old_pos = p->dicPos;
+  if (!lzb_cuda_ok(cudaMemcpy(&st, ctl->d_state, sizeof st, cudaMemcpyDeviceToHost), "D2H state")) return SZ_ERROR_FAIL;
+  if (st.dic_pos > old_pos &&
+      !lzb_cuda_ok(cudaMemcpy(p->dic + old_pos, ctl->d_dic + old_pos, st.dic_pos - old_pos, cudaMemcpyDeviceToHost), "D2H dictionary"))
+    return SZ_ERROR_FAIL;
+
+  /* scalars back into the reference's fields */
+  p->range = st.range; p->code = st.code; p->state = st.state;
+  for (int i = 0; i < 4; i++) p->reps[i] = st.rep[i];
+  p->processedPos = st.total_pos; p->checkDicSize = st.dict_full; p->remainLen = st.pending;
+  p->needFlush = (st.flags & 1) ? 1 : 0; p->needInitState = (st.flags & 2) ? 1 : 0;
+  p->dicPos = st.dic_pos;
+  p->prop.lc = st.lc; p->prop.lp = st.lp; p->prop.pb = st.pb;
+  if (l2)
+  {
+    l2->state = (int)st.l2_phase; l2->control = (Byte)st.l2_control;
+    l2->packSize = st.l2_pack_left; l2->unpackSize = st.l2_unpack_left;
+    l2->needInitDic = (st.l2_flags & 1) ? 1 : 0; l2->needInitState = (st.l2_flags & 2) ? 1 : 0; l2->needInitProp = (st.l2_flags & 4) ? 1 : 0;
+  }
+
+  /* input accounting: what the reference parks in tempBuf (LzmaDec.c:734-740,779-786) */
+  const size_t used = x.src_used;
+  if (x.status == LZMA_STATUS_NEEDS_MORE_INPUT && st.held > 0 && used == total_in)
+  {
+    Byte keep[LZMA_REQUIRED_INPUT_MAX];
+    const unsigned h = st.held;                           /* <= 19 */
+    for (unsigned i = 0; i < h; i++)
+    {
+      const size_t at = total_in - h + i;                 /* index in (tempBuf || src) */
+      keep[i] = at < prefix ? p->tempBuf[at] : src[at - prefix];
+    }
+    memcpy(p->tempBuf, keep, h);
+    p->tempBufSize = h;
+    *srcLen = inSize;
+  }
+  else if (used >= prefix)
+  {
+    p->tempBufSize = 0;
+    *srcLen = used - prefix;
+  }
+  else
+    *srcLen = 0;                                          /* nothing consumed: parked bytes stay parked */
+  *status = (ELzmaStatus)x.status;
+  return x.res;
 }
 
 extern "C" SRes LzmaDec_DecodeToDic(CLzmaDec *p, SizeT dicLimit, const Byte *src, SizeT *srcLen,
                                     ELzmaFinishMode finishMode, ELzmaStatus *status)
 {
-  const SizeT inSize = *srcLen;
-  *srcLen = 0;
-  *status = LZMA_STATUS_NOT_SPECIFIED;
-  SRes r = need_fresh(p, "LzmaDec_DecodeToDic");
-  if (r != SZ_OK) return r;
-  if (dicLimit > p->dicBufSize) return SZ_ERROR_PARAM;
-  if (inSize > 0xFFFFFFFFull || dicLimit > 0xFFFFFFFFull) return SZ_ERROR_UNSUPPORTED;
-  LzbContext *c = lzb_default_context();
-  if (!c) return SZ_ERROR_FAIL;
-  LzbUnit u;
-  LzbResult x;
-  memset(&u, 0, sizeof u);
-  u.src_len = (uint32_t)inSize; u.dst_cap = (uint32_t)dicLimit; u.dict_size = p->prop.dicSize;
-  u.codec = LZB_CODEC_LZMA; u.lc = (uint8_t)p->prop.lc; u.lp = (uint8_t)p->prop.lp; u.pb = (uint8_t)p->prop.pb;
-  u.finish = (uint8_t)finishMode;
-  if (inSize < 5)
-  {
-    /* LzmaDec.c:732-740: the bytes are parked in tempBuf and more input is requested */
-    memcpy(p->tempBuf, src, inSize);
-    p->tempBufSize = (unsigned)inSize;
-    *srcLen = inSize;
-    *status = LZMA_STATUS_NEEDS_MORE_INPUT;
-    ctl_of(p)->used = 1;
-    return SZ_OK;
-  }
-  r = Lzb_DecodeUnitsHost(c, src, inSize, p->dic, dicLimit, &u, &x, 1);
-  if (r != SZ_OK) return r;
-  ctl_of(p)->used = 1;
-  *srcLen = x.src_used;
-  p->dicPos = x.dst_done;
-  p->processedPos = x.dst_done;
-  p->needFlush = 0;
-  p->needInitState = 0;
-  *status = (ELzmaStatus)x.status;
-  /* the one-call driver folds NEEDS_MORE_INPUT into SZ_ERROR_INPUT_EOF (LzmaDec.c:996-997); undo that */
-  if (x.res == SZ_ERROR_INPUT_EOF) return SZ_OK;
-  return x.res;
+  return step(p, nullptr, dicLimit, src, srcLen, finishMode, status, "LzmaDec_DecodeToDic");
 }
 
 extern "C" SRes LzmaDec_DecodeToBuf(CLzmaDec *p, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
                                     ELzmaFinishMode finishMode, ELzmaStatus *status)
 {
-  /* reference LzmaDec.c:840-878, for a decoder right after LzmaDec_Init and an output that fits the
-   * dictionary buffer (one slice of the reference's loop) */
-  const SizeT outSize = *destLen;
-  SizeT inSize = *srcLen;
+  /* reference LzmaDec.c:840-878: decode into the ring dictionary slice by slice, copy each slice out */
+  SizeT outSize = *destLen, inSize = *srcLen;
   *srcLen = *destLen = 0;
-  if (outSize > p->dicBufSize)
+  for (;;)
   {
-    lzb_set_error("LzmaDec_DecodeToBuf: output larger than the dictionary buffer needs the resumable path (next round)");
-    *status = LZMA_STATUS_NOT_SPECIFIED;
-    return SZ_ERROR_UNSUPPORTED;
+    SizeT inCur = inSize, outCur, dicPos;
+    ELzmaFinishMode mode;
+    if (p->dicPos == p->dicBufSize) p->dicPos = 0;
+    dicPos = p->dicPos;
+    if (outSize > p->dicBufSize - dicPos) { outCur = p->dicBufSize; mode = LZMA_FINISH_ANY; }
+    else { outCur = dicPos + outSize; mode = finishMode; }
+    SRes res = LzmaDec_DecodeToDic(p, outCur, src, &inCur, mode, status);
+    src += inCur; inSize -= inCur; *srcLen += inCur;
+    outCur = p->dicPos - dicPos;
+    memcpy(dest, p->dic + dicPos, outCur);
+    dest += outCur; outSize -= outCur; *destLen += outCur;
+    if (res != 0) return res;
+    if (outCur == 0 || outSize == 0) return SZ_OK;
   }
-  SRes r = LzmaDec_DecodeToDic(p, outSize, src, &inSize, finishMode, status);
-  *srcLen = inSize;
-  if (r == SZ_ERROR_UNSUPPORTED || r == SZ_ERROR_PARAM || r == SZ_ERROR_FAIL) return r;
-  memcpy(dest, p->dic, p->dicPos);
-  *destLen = p->dicPos;
-  return r;
 }
 
 /* ------------------------------------------------------------------ LZMA2 state interface ----- */
@@ -189,7 +270,6 @@ static void lzma2_old_props(Byte prop, Byte *p5)
   p5[1] = (Byte)dict; p5[2] = (Byte)(dict >> 8); p5[3] = (Byte)(dict >> 16); p5[4] = (Byte)(dict >> 24);
 }
 
-/* the LZMA2 dictionary byte is kept in the otherwise unused CLzma2Dec.control until decoding starts */
 extern "C" SRes Lzma2Dec_AllocateProbs(CLzma2Dec *p, Byte prop, ISzAlloc *alloc)
 {
   Byte p5[LZMA_PROPS_SIZE];
@@ -228,41 +308,56 @@ extern "C" SRes Lzma2Dec_DecodeToDic(CLzma2Dec *p, SizeT dicLimit, const Byte *s
                                      ELzmaFinishMode finishMode, ELzmaStatus *status)
 {
   CLzmaDec *d = &p->decoder;
-  const SizeT inSize = *srcLen;
-  *srcLen = 0;
-  *status = LZMA_STATUS_NOT_SPECIFIED;
-  SRes r = need_fresh(d, "Lzma2Dec_DecodeToDic");
-  if (r != SZ_OK) return r;
-  if (p->state != 0 || !p->needInitDic) { lzb_set_error("Lzma2Dec_DecodeToDic: Lzma2Dec_Init was not called"); return SZ_ERROR_UNSUPPORTED; }
-  if (dicLimit > d->dicBufSize) return SZ_ERROR_PARAM;
-  SizeT dl = dicLimit, sl = inSize;
-  r = Lzma2DecodeParallel(nullptr, d->dic, &dl, src, &sl, lzma2_prop_from_dict(d->prop.dicSize), finishMode, status);
-  if (r == SZ_ERROR_FAIL || r == SZ_ERROR_MEM) return r;
-  ctl_of(d)->used = 1;
-  d->needFlush = 0;
-  d->dicPos = dl;
-  d->processedPos = (UInt32)dl;
-  *srcLen = sl;
-  return r;
+  /* A decoder right after Lzma2Dec_Init that is handed a buffer holding many dictionary-reset groups is
+   * the 7zDec.c:175-222 whole-folder case: decode the groups in parallel (lzb_containers.cu).  Anything
+   * else -- partial input, continuation -- takes the resumable single-unit path. */
+  if (p->state == 0 && p->needInitDic && p->needInitState && p->needInitProp && d->needFlush && d->dicPos == 0 &&
+      d->tempBufSize == 0 && d->probs && d->dic && dicLimit <= d->dicBufSize && *srcLen >= (1u << 20))
+  {
+    size_t n = 0, end = 0;
+    int eos = 0;
+    LzbUnit probe[2];
+    const Byte prop = lzma2_prop_from_dict(d->prop.dicSize);
+    if (Lzma2_IndexUnits(src, *srcLen, prop, probe, 2, &n, &end, &eos) == SZ_OK && n >= 2 && eos)
+    {
+      SizeT dl = dicLimit, sl = *srcLen;
+      SRes r = Lzma2DecodeParallel(nullptr, d->dic, &dl, src, &sl, prop, finishMode, status);
+      if (r == SZ_OK && *status == LZMA_STATUS_FINISHED_WITH_MARK)
+      {
+        *srcLen = sl;
+        d->dicPos = dl; d->processedPos = (UInt32)dl; d->needFlush = 0;
+        p->state = 8 /* LZMA2_STATE_FINISHED */;
+        p->needInitDic = p->needInitState = p->needInitProp = 0;
+        return r;
+      }
+      /* not a clean whole-stream decode: fall through to the sequential path, which reproduces the
+       * reference's exact stopping point and leaves a resumable object behind */
+    }
+  }
+  return step(d, p, dicLimit, src, srcLen, finishMode, status, "Lzma2Dec_DecodeToDic");
 }
 
 extern "C" SRes Lzma2Dec_DecodeToBuf(CLzma2Dec *p, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
                                      ELzmaFinishMode finishMode, ELzmaStatus *status)
 {
-  /* reference Lzma2Dec.c:291-328, one slice (output must fit the dictionary buffer) */
-  const SizeT outSize = *destLen;
-  SizeT inSize = *srcLen;
+  /* reference Lzma2Dec.c:291-328 */
+  SizeT outSize = *destLen, inSize = *srcLen;
+  CLzmaDec *d = &p->decoder;
   *srcLen = *destLen = 0;
-  if (outSize > p->decoder.dicBufSize)
+  for (;;)
   {
-    lzb_set_error("Lzma2Dec_DecodeToBuf: output larger than the dictionary buffer needs the resumable path (next round)");
-    *status = LZMA_STATUS_NOT_SPECIFIED;
-    return SZ_ERROR_UNSUPPORTED;
+    SizeT inCur = inSize, outCur, dicPos;
+    ELzmaFinishMode mode;
+    if (d->dicPos == d->dicBufSize) d->dicPos = 0;
+    dicPos = d->dicPos;
+    if (outSize > d->dicBufSize - dicPos) { outCur = d->dicBufSize; mode = LZMA_FINISH_ANY; }
+    else { outCur = dicPos + outSize; mode = finishMode; }
+    SRes res = Lzma2Dec_DecodeToDic(p, outCur, src, &inCur, mode, status);
+    src += inCur; inSize -= inCur; *srcLen += inCur;
+    outCur = d->dicPos - dicPos;
+    memcpy(dest, d->dic + dicPos, outCur);
+    dest += outCur; outSize -= outCur; *destLen += outCur;
+    if (res != 0) return res;
+    if (outCur == 0 || outSize == 0) return SZ_OK;
   }
-  SRes r = Lzma2Dec_DecodeToDic(p, outSize, src, &inSize, finishMode, status);
-  *srcLen = inSize;
-  if (r == SZ_ERROR_UNSUPPORTED || r == SZ_ERROR_PARAM || r == SZ_ERROR_FAIL) return r;
-  memcpy(dest, p->decoder.dic, p->decoder.dicPos);
-  *destLen = p->decoder.dicPos;
-  return r;
 }

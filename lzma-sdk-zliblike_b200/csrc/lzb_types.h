@@ -16,7 +16,29 @@ extern "C" {
 enum { LZB_CODEC_LZMA = 0, LZB_CODEC_LZMA2 = 1 };
 enum { LZB_FILTER_NONE = 0, LZB_FILTER_DELTA = 3, LZB_FILTER_X86 = 4 };   /* xz filter ids, Xz.h:11-19 */
 enum { LZB_CHECK_NONE = 0, LZB_CHECK_CRC32 = 1, LZB_CHECK_CRC64 = 4 };     /* xz check ids, Xz.h:66-69 */
-enum { LZB_UNIT_VERIFY = 1 };  /* flags: compare the computed digest with `expect` -> SZ_ERROR_CRC */
+enum
+{
+  LZB_UNIT_VERIFY = 1,       /* compare the computed digest with `expect` -> SZ_ERROR_CRC              */
+  LZB_UNIT_X86_ENCODE = 2,   /* stand-alone x86_Convert: encoding direction                          */
+  LZB_UNIT_POST_REPORT = 4,  /* stand-alone filter call: report processed count / history in result  */
+  LZB_UNIT_STATEFUL = 8      /* resumable decoder: `expect` = device address of an LzbStreamState,
+                                `filter_param` = dicBufSize (ring size), `dst_cap` = dicLimit         */
+};
+
+/* Device-resident state of a resumable decoder (the SDK's CLzmaDec / CLzma2Dec between calls).
+ * Scalars mirror the reference fields; the probability model follows the 128-byte header. */
+typedef struct LzbStreamState
+{
+  uint32_t range, code, state, rep[4];            /* CLzmaDec.range/code/state/reps          */
+  uint32_t total_pos, dict_full, pending;         /* processedPos, checkDicSize, remainLen   */
+  uint32_t flags;                                 /* bit0 needFlush, bit1 needInitState      */
+  uint32_t dic_pos;                               /* dicPos in, dicPos out                   */
+  uint32_t held;                                  /* in: bytes re-presented from tempBuf; out: bytes to keep */
+  uint32_t lc, lp, pb;
+  uint32_t l2_phase, l2_control, l2_pack_left, l2_unpack_left;   /* CLzma2Dec.state/control/packSize/unpackSize */
+  uint32_t l2_flags;                              /* bit0 needInitDic, bit1 needInitState, bit2 needInitProp */
+  uint32_t reserved[11];
+} LzbStreamState;                                 /* 128 bytes */
 
 typedef struct LzbUnit
 {

@@ -205,6 +205,43 @@ int refh_lzma2_decode(uint8_t *dst, size_t dstCap, size_t *dstLen, const uint8_t
   return r;
 }
 
+/* zlib-like buffer interface of the LZMA2 layer, fed/drained in chunks (XzDec.c:285-298 pattern) */
+int refh_lzma2_decode_tobuf(uint8_t *dst, size_t dstCap, size_t *dstLen, const uint8_t *src, size_t srcLen,
+                            size_t *srcUsed, uint8_t prop, size_t in_chunk, size_t out_chunk,
+                            int finishModeAtEnd, int *status)
+{
+  CLzma2Dec d;
+  SRes r;
+  size_t ip = 0, op = 0;
+  ELzmaStatus st = LZMA_STATUS_NOT_SPECIFIED;
+  Lzma2Dec_Construct(&d);
+  r = Lzma2Dec_Allocate(&d, prop, &g_alloc);
+  if (r != SZ_OK) { *dstLen = 0; *srcUsed = 0; *status = 0; return r; }
+  Lzma2Dec_Init(&d);
+  for (;;)
+  {
+    size_t inAvail = srcLen - ip < in_chunk ? srcLen - ip : in_chunk;
+    size_t inLeft = inAvail, inPos = 0;
+    int progressed = 0, done = 0;
+    for (;;)
+    {
+      SizeT il = inLeft, ol = dstCap - op < out_chunk ? dstCap - op : out_chunk;
+      ELzmaFinishMode fm = (ol == dstCap - op) ? (ELzmaFinishMode)finishModeAtEnd : LZMA_FINISH_ANY;
+      r = Lzma2Dec_DecodeToBuf(&d, dst + op, &ol, src + ip + inPos, &il, fm, &st);
+      inPos += il; inLeft -= il; op += ol;
+      if (il || ol) progressed = 1;
+      if (r != SZ_OK || st == LZMA_STATUS_FINISHED_WITH_MARK || op == dstCap) { done = 1; break; }
+      if (inLeft == 0 || (il == 0 && ol == 0)) break;
+    }
+    ip += inPos;
+    if (done) break;
+    if (ip == srcLen && (!progressed || st == LZMA_STATUS_NEEDS_MORE_INPUT)) break;
+  }
+  *dstLen = op; *srcUsed = ip; *status = (int)st;
+  Lzma2Dec_Free(&d, &g_alloc);
+  return r;
+}
+
 /* ---------------- multi-threaded helpers (pthread) ---------------- */
 typedef struct
 {

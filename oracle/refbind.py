@@ -74,6 +74,9 @@ class _Ref:
                                         C.c_int, C.c_int, C.c_int, _u8p]
         L.refh_lzma2_decode.restype = C.c_int
         L.refh_lzma2_decode.argtypes = [_u8p, C.c_size_t, _szp, _u8p, _szp, C.c_uint8, C.c_int, _ip]
+        L.refh_lzma2_decode_tobuf.restype = C.c_int
+        L.refh_lzma2_decode_tobuf.argtypes = [_u8p, C.c_size_t, _szp, _u8p, C.c_size_t, _szp, C.c_uint8,
+                                              C.c_size_t, C.c_size_t, C.c_int, _ip]
         L.refh_decode_batch_mt.restype = C.c_double
         L.refh_decode_batch_mt.argtypes = [C.c_int, C.c_size_t, _u8p, _u64p, _u32p, _u8p, _u64p, _u32p, _u8p,
                                            C.c_int, _i32p, _i32p, _u32p, _u32p, C.c_int, C.c_int]
@@ -159,6 +162,16 @@ class _Ref:
         r = self.L.refh_lzma2_decode(_ptr(dst), dest_cap, C.byref(dl), _ptr(src), C.byref(sl), prop, finish_mode,
                                      C.byref(st))
         return dict(res=r, status=st.value, dest_len=dl.value, src_len=sl.value, out=dst[:dest_cap])
+
+    def lzma2_decode_tobuf(self, packed, prop, dest_cap, in_chunk, out_chunk, finish_at_end=0):
+        src = as_u8(packed)
+        dst = np.zeros(max(dest_cap, 1), dtype=np.uint8)
+        dl = C.c_size_t(0)
+        su = C.c_size_t(0)
+        st = C.c_int(0)
+        r = self.L.refh_lzma2_decode_tobuf(_ptr(dst), dest_cap, C.byref(dl), _ptr(src), len(src), C.byref(su), prop,
+                                           in_chunk, out_chunk, finish_at_end, C.byref(st))
+        return dict(res=r, status=st.value, dest_len=dl.value, src_len=su.value, out=dst[:dest_cap])
 
     # ---- batches ----
     def decode_batch_mt(self, kind, src, src_off, src_len, dst_off, dst_cap, props, finish_mode, threads,
@@ -289,6 +302,44 @@ def ref() -> _Ref:
     return _ref
 
 
+def drive_tobuf(to_buf, src, dst, dest_cap, in_chunk, out_chunk, finish_at_end):
+    """The chunked feed/drain loop of refh_lzma_decode_tobuf (oracle/ref_harness.c), over any
+    ``to_buf(dest_ptr, &destLen, src_ptr, &srcLen, finishMode, &status)`` callable."""
+    ip = op = 0
+    st = C.c_int(0)
+    n = len(src)
+    r = 0
+    done = False
+    while not done:
+        in_left = min(n - ip, in_chunk)
+        in_pos = 0
+        progressed = False
+        while True:
+            il = C.c_size_t(in_left)
+            ol_req = min(dest_cap - op, out_chunk)
+            ol = C.c_size_t(ol_req)
+            fm = finish_at_end if ol_req == dest_cap - op else 0
+            dptr = dst[op:].ctypes.data_as(_u8p) if op < len(dst) else _ptr(dst)
+            sptr = src[ip + in_pos:].ctypes.data_as(_u8p) if ip + in_pos < n else _ptr(src if n else dst)
+            r = to_buf(dptr, C.byref(ol), sptr, C.byref(il), fm, C.byref(st))
+            in_pos += il.value
+            in_left -= il.value
+            op += ol.value
+            if il.value or ol.value:
+                progressed = True
+            if r != 0 or st.value == 1 or op == dest_cap:
+                done = True
+                break
+            if in_left == 0 or (il.value == 0 and ol.value == 0):
+                break
+        ip += in_pos
+        if done:
+            break
+        if ip == n and (not progressed or st.value == 3):
+            break
+    return dict(res=r, status=st.value, dest_len=op, src_len=ip, out=dst[:dest_cap])
+
+
 class OraUnit(C.Structure):
     _fields_ = [("src_off", C.c_uint64), ("src_len", C.c_uint64), ("unpack_len", C.c_uint64),
                 ("n_chunks", C.c_uint32), ("max_lclp", C.c_uint32)]
@@ -343,6 +394,14 @@ class _Oracle:
         L.ora_lzma_free.argtypes = [C.c_void_p]
         L.ora_lzma_to_buf.restype = C.c_int
         L.ora_lzma_to_buf.argtypes = [C.c_void_p, _u8p, _szp, _u8p, _szp, C.c_int, _ip]
+        L.ora_lzma2_alloc.restype = C.c_int
+        L.ora_lzma2_alloc.argtypes = [C.c_void_p, C.c_uint8]
+        L.ora_lzma2_reset.restype = None
+        L.ora_lzma2_reset.argtypes = [C.c_void_p]
+        L.ora_lzma2_free.restype = None
+        L.ora_lzma2_free.argtypes = [C.c_void_p]
+        L.ora_lzma2_to_buf.restype = C.c_int
+        L.ora_lzma2_to_buf.argtypes = [C.c_void_p, _u8p, _szp, _u8p, _szp, C.c_int, _ip]
 
     def lzma_decode(self, packed, props, dest_cap, finish_mode=0):
         src = as_u8(packed)
@@ -366,39 +425,22 @@ class _Oracle:
         if r != 0:
             return dict(res=r, status=0, dest_len=0, src_len=0, out=dst[:dest_cap])
         self.L.ora_lzma_reset(sp)
-        ip = op = 0
-        st = C.c_int(0)
-        n = len(src)
-        done = False
-        while not done:
-            in_left = min(n - ip, in_chunk)
-            in_pos = 0
-            progressed = False
-            while True:
-                il = C.c_size_t(in_left)
-                ol_req = min(dest_cap - op, out_chunk)
-                ol = C.c_size_t(ol_req)
-                fm = finish_at_end if ol_req == dest_cap - op else 0
-                r = self.L.ora_lzma_to_buf(sp, dst[op:].ctypes.data_as(_u8p) if op < len(dst) else _ptr(dst),
-                                           C.byref(ol), src[ip + in_pos:].ctypes.data_as(_u8p) if ip + in_pos < n else _ptr(src),
-                                           C.byref(il), fm, C.byref(st))
-                in_pos += il.value
-                in_left -= il.value
-                op += ol.value
-                if il.value or ol.value:
-                    progressed = True
-                if r != 0 or st.value == 1 or op == dest_cap:
-                    done = True
-                    break
-                if in_left == 0 or (il.value == 0 and ol.value == 0):
-                    break
-            ip += in_pos
-            if done:
-                break
-            if ip == n and (not progressed or st.value == 3):
-                break
+        out = drive_tobuf(lambda *a: self.L.ora_lzma_to_buf(sp, *a), src, dst, dest_cap, in_chunk, out_chunk, finish_at_end)
         self.L.ora_lzma_free(sp)
-        return dict(res=r, status=st.value, dest_len=op, src_len=ip, out=dst[:dest_cap])
+        return out
+
+    def lzma2_decode_tobuf(self, packed, prop, dest_cap, in_chunk, out_chunk, finish_at_end=0):
+        src = as_u8(packed)
+        dst = np.zeros(max(dest_cap, 1), dtype=np.uint8)
+        stt = _OraLzmaState()
+        sp = C.addressof(stt)
+        r = self.L.ora_lzma2_alloc(sp, prop)
+        if r != 0:
+            return dict(res=r, status=0, dest_len=0, src_len=0, out=dst[:dest_cap])
+        self.L.ora_lzma2_reset(sp)
+        out = drive_tobuf(lambda *a: self.L.ora_lzma2_to_buf(sp, *a), src, dst, dest_cap, in_chunk, out_chunk, finish_at_end)
+        self.L.ora_lzma2_free(sp)
+        return out
 
     def lzma2_decode(self, packed, prop, dest_cap, finish_mode=1):
         src = as_u8(packed)

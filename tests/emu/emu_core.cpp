@@ -41,9 +41,11 @@ extern "C" int emu_decode_units(const uint8_t *packed, uint8_t *out, const LzbUn
     if (np * 2 < lzb::kPostScratchBytes) np = lzb::kPostScratchBytes / 2;
     probs.assign(np, 0xDEAD);
     lzb::UnitDecoder d;
-    d.begin(packed + u.src_off, u.src_len, out + u.dst_off, u.dst_cap, u.dict_size, probs.data());
-    lzb::decode_unit(d, u, r);
-    lzb::post_process(u, r, out + u.dst_off, (uint8_t *)probs.data());
+    const bool stateful = (u.flags & LZB_UNIT_STATEFUL) != 0;
+    d.begin(packed + u.src_off, u.src_len, out + u.dst_off, stateful ? u.filter_param : u.dst_cap, u.dict_size,
+            probs.data());
+    lzb::decode_unit(d, u, r, stateful ? reinterpret_cast<LzbStreamState *>((uintptr_t)u.expect) : nullptr);
+    if (!stateful) lzb::post_process(u, r, out + u.dst_off, (uint8_t *)probs.data());
     results[i] = r;
   }
   return 0;

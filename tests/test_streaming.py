@@ -1,0 +1,114 @@
+"""The zlib-like resumable contract: LzmaDec_DecodeToBuf / Lzma2Dec_DecodeToBuf fed and
+drained in arbitrary chunk sizes must give what the reference gives -- same bytes, same final
+(SRes, status, destLen, srcLen) -- for valid, truncated and corrupted streams.
+
+CPU part : oracle vs reference (pins the oracle's streaming), and the device code's resume logic under
+           emulation (tests/streamdrive.EmuStream) vs the oracle.
+GPU part : the real C-ABI objects on the B200 vs the oracle.
+"""
+import numpy as np
+import pytest
+
+import cases
+from streamdrive import EmuStream, GpuStream
+
+CHUNKINGS = ((1, 1 << 20), (7, 13), (1000, 777), (1 << 20, 1), (19, 4096), (64, 64), (1 << 20, 1 << 20), (5, 5), (20, 21))
+
+
+def same(a, b):
+    for f in ("res", "status", "dest_len", "src_len"):
+        assert a[f] == b[f], (f, {k: a[k] for k in a if k != "out"}, {k: b[k] for k in b if k != "out"})
+    assert np.array_equal(a["out"][: a["dest_len"]], b["out"][: b["dest_len"]])
+
+
+def lzma_streams(limit=None):
+    blobs, _ = cases.golden()
+    out = []
+    for c in cases.cases_of("lzma"):
+        if c["mut"] is None and c["finish"] == 0 and c["res"] == 0 and c["out_crc"] == c["plain_crc"] and c["dest_len"] == c["cap"]:
+            out.append((blobs[c["blob"]], bytes.fromhex(c["props"]), c["cap"]))
+    return out[:limit] if limit else out
+
+
+def lzma2_streams():
+    blobs, _ = cases.golden()
+    seen, out = set(), []
+    for c in cases.cases_of("lzma2"):
+        if c["mut"] is None and c["blob"] not in seen and c["res"] == 0 and c["finish"] == 1 and c["status"] == 1:
+            seen.add(c["blob"])
+            out.append((blobs[c["blob"]], c["prop"], c["dest_len"]))
+    return out
+
+
+def run_matrix(impl, want, streams2=True, heavy=False):
+    rng = np.random.default_rng(31)
+    for packed, props, n in lzma_streams():
+        for ic, oc in CHUNKINGS:
+            if not heavy and n > 30000 and min(ic, oc) < 19:
+                continue
+            for fm in (0, 1):
+                same(want.lzma_decode_tobuf(packed, props, n, ic, oc, fm), impl.lzma_decode_tobuf(packed, props, n, ic, oc, fm))
+        if len(packed) > 40:
+            for _ in range(3):
+                bad = packed.copy()
+                bad[int(rng.integers(5, len(bad)))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+                cut = int(rng.integers(0, len(bad)))
+                for blob in (bad, packed[:cut]):
+                    a, b = want.lzma_decode_tobuf(blob, props, n, 997, 4096, 1), impl.lzma_decode_tobuf(blob, props, n, 997, 4096, 1)
+                    # the first unrecoverable call decides res; partial output before an error is chunk-dependent
+                    assert a["res"] == b["res"] and (a["res"] != 0 or (a["status"], a["dest_len"], a["src_len"]) ==
+                                                     (b["status"], b["dest_len"], b["src_len"]))
+    if not streams2:
+        return
+    for packed, prop, n in lzma2_streams():
+        for ic, oc in ((1 << 20, 1 << 20), (1000, 777), (4096, 1 << 20), (1 << 20, 5000), (3, 100000) if n < 100000 else (333, 65536)):
+            for fm in (0, 1):
+                same(want.lzma2_decode_tobuf(packed, prop, n, ic, oc, fm), impl.lzma2_decode_tobuf(packed, prop, n, ic, oc, fm))
+        same(want.lzma2_decode_tobuf(packed[:-1], prop, n, 5000, 5000, 1), impl.lzma2_decode_tobuf(packed[:-1], prop, n, 5000, 5000, 1))
+        same(want.lzma2_decode_tobuf(packed, prop, n // 2, 5000, 3000, 0), impl.lzma2_decode_tobuf(packed, prop, n // 2, 5000, 3000, 0))
+
+
+@pytest.mark.needref
+def test_oracle_streaming_pinned_to_reference(ref, ora):
+    run_matrix(ora, ref)
+
+
+def test_kernel_resume_logic_under_emulation(ora):
+    run_matrix(EmuStream(), ora)
+
+
+@pytest.mark.gpu
+def test_gpu_stateful_objects(ora):
+    run_matrix(GpuStream(), ora)
+
+
+@pytest.mark.gpu
+def test_gpu_lzma2_whole_buffer_goes_parallel_and_matches(ora):
+    """Lzma2Dec_DecodeToDic on a fresh object with a multi-unit buffer takes the parallel path; result and
+    object state must be those of the sequential decoder."""
+    import ctypes as C
+    from streamdrive import CLzma2Dec, _alloc
+    import lzb200
+    g = GpuStream()
+    L = g.L
+    L.Lzma2Dec_AllocateProbs.restype = C.c_int
+    L.Lzma2Dec_AllocateProbs.argtypes = [C.c_void_p, C.c_uint8, C.c_void_p]
+    L.Lzma2Dec_DecodeToDic.restype = C.c_int
+    L.Lzma2Dec_DecodeToDic.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.c_int, C.POINTER(C.c_int)]
+    L.LzmaDec_FreeProbs.argtypes = [C.c_void_p, C.c_void_p]
+    blobs, _ = cases.golden()
+    prop = [c["prop"] for c in cases.cases_of("lzma2") if c["blob"] == "lzma2_multi"][0]
+    one = blobs["lzma2_multi"][:-1]
+    blob = np.concatenate([one] * 4 + [np.zeros(1, np.uint8)])        # 16 units, > 1 MiB packed? no: force the path
+    total = 360000 * 4
+    want = ora.lzma2_decode(blob, prop, total, 1)
+    d = CLzma2Dec()
+    assert L.Lzma2Dec_AllocateProbs(C.byref(d), prop, C.byref(_alloc)) == 0
+    out = np.zeros(total, np.uint8)
+    d.decoder.dic, d.decoder.dicBufSize = out.ctypes.data, total        # 7zDec.c:185-186
+    L.Lzma2Dec_Init(C.byref(d))
+    sl, st = C.c_size_t(len(blob)), C.c_int(0)
+    r = L.Lzma2Dec_DecodeToDic(C.byref(d), total, blob.ctypes.data, C.byref(sl), 1, C.byref(st))
+    assert (r, st.value, d.decoder.dicPos, sl.value) == (want["res"], want["status"], want["dest_len"], want["src_len"])
+    assert np.array_equal(out, want["out"])
+    L.LzmaDec_FreeProbs(C.byref(d.decoder), C.byref(_alloc))

@@ -236,7 +236,7 @@ def main():
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local = env_int("LOCAL_RANK", 0)
     cache = os.environ.get("LZB_BENCH_CACHE", "/tmp/lzb_bench_cache")
-    default_units = {"lzma64k": 65536, "lzma2_1m": 8192, "xz4m": 1024}[a.workload]
+    default_units = {"lzma64k": 65536, "lzma2_1m": 8192, "xz4m": 2220}[a.workload]   # xz4m: one 4 MiB block per resident warp
     n_units = a.units or (default_units // 16 if a.small else default_units)
     threads = host_threads()
     cfg = dict(workload=WORKLOADS[a.workload], units_per_gpu=n_units, sharding="static, units split by rank, no collective",

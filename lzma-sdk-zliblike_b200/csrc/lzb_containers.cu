@@ -156,18 +156,21 @@ extern "C" SRes Lzma2DecodeParallel(LzbContext *c, Byte *dest, SizeT *destLen, c
   r = Lzb_DecodeUnitsHost(c, src, in_size, dest, cap, w.units.data(), res.data(), w.units.size());
   if (r != SZ_OK) return r;
   size_t done = 0;
+  int carried = LZMA_STATUS_NOT_SPECIFIED;               /* *status is sticky across chunks in the reference */
   for (size_t k = 0; k < w.units.size(); k++)
   {
     const LzbUnit &u = w.units[k];
     const LzbResult &x = res[k];
     done += x.dst_done;
+    if (x.status != LZB_ST_INHERIT) carried = x.status;
     const bool last = k + 1 == w.units.size();
-    const bool clean = x.res == SZ_OK && x.status == LZMA_STATUS_NOT_FINISHED && x.dst_done == u.dst_cap;
+    const bool clean = x.res == SZ_OK && x.dst_done == u.dst_cap && carried != LZMA_STATUS_NEEDS_MORE_INPUT &&
+                       carried != LZMA_STATUS_FINISHED_WITH_MARK;
     if (last || !clean)
     {
       *destLen = done;
       *srcLen = (size_t)u.src_off + x.src_used;
-      *status = (ELzmaStatus)x.status;
+      *status = (ELzmaStatus)carried;
       return x.res;
     }
   }
@@ -532,7 +535,8 @@ extern "C" SRes XzDecodeParallel(LzbContext *c, Byte *dest, SizeT *destLen, cons
       done += x.dst_done;
       bool clean;
       if (b.complete && lastu) clean = x.res == SZ_OK && x.status == LZMA_STATUS_FINISHED_WITH_MARK;
-      else if (!lastu) clean = x.res == SZ_OK && x.status == LZMA_STATUS_NOT_FINISHED && x.dst_done == u.dst_cap;
+      else if (!lastu) clean = x.res == SZ_OK && x.dst_done == u.dst_cap && x.status != LZMA_STATUS_NEEDS_MORE_INPUT &&
+                               x.status != LZMA_STATUS_FINISHED_WITH_MARK;
       else clean = false;                                /* cut-short block: its last unit ends the call */
       if (!clean)
       {

@@ -774,11 +774,11 @@ LZB_FN void decode_unit(UnitDecoder &d, const LzbUnit &u, LzbResult &r, LzbStrea
   uint32_t at_in = 0, pack_left = 0, unpack_left = 0, control = 0;
   int phase = PH_CONTROL;
   bool want_dic = true, want_state = true, want_props = true;
-  int status = LZB_ST_NOT_SPECIFIED, res = LZB_SZ_OK;
+  int status = LZB_ST_INHERIT, res = LZB_SZ_OK;
   r.check = 0;
   if (raw)
   {
-    if (!st && in_size < 5) { r.res = LZB_SZ_ERROR_INPUT_EOF; r.status = status; r.src_used = 0; r.dst_done = 0; return; }
+    if (!st && in_size < 5) { r.res = LZB_SZ_ERROR_INPUT_EOF; r.status = LZB_ST_NOT_SPECIFIED; r.src_used = 0; r.dst_done = 0; return; }
     d.set_props(u.lc, u.lp, u.pb);
     control = 0x80; phase = PH_DATA_MORE; pack_left = in_size; unpack_left = 0xFFFFFFFFu;
   }
@@ -805,7 +805,7 @@ LZB_FN void decode_unit(UnitDecoder &d, const LzbUnit &u, LzbResult &r, LzbStrea
     /* finish == 2 (host-internal "unit" mode): like FINISH_END inside the unit's last chunk, so that its
      * proper termination is still verified, but stop at the unit's end instead of reading the next header */
     if (!raw && at == dic_limit && (finish == 0 || (finish == 2 && phase == PH_CONTROL)))
-    { status = LZB_ST_NOT_FINISHED; break; }
+    { if (finish == 0) status = LZB_ST_NOT_FINISHED; break; }   /* unit mode: a boundary is not a stop of the stream */
 
     if (phase != PH_DATA && phase != PH_DATA_MORE)
     {

@@ -183,7 +183,9 @@ extern "C" SRes Lzb_DecodeUnitsDevice(LzbContext *c, const Byte *d_packed, Byte 
 /* ------------------------------------------------------------------ host-arena batch --------- */
 struct Slice { size_t first, count; uint64_t src_lo, src_hi, dst_lo, dst_hi; };
 
-static void make_slices(const LzbUnit *u, size_t n, std::vector<Slice> &out)
+/* A slice is the granule of H2D / kernel / D2H overlap.  It must still hold at least one unit per
+ * resident warp (min_units), otherwise its kernel leaves the GPU partly idle. */
+static void make_slices(const LzbUnit *u, size_t n, size_t min_units, std::vector<Slice> &out)
 {
   uint64_t total = 0;
   for (size_t i = 0; i < n; i++) total += u[i].dst_cap;
@@ -197,7 +199,7 @@ static void make_slices(const LzbUnit *u, size_t n, std::vector<Slice> &out)
     s.first = i; s.count = 0;
     s.src_lo = s.dst_lo = ~0ull; s.src_hi = s.dst_hi = 0;
     uint64_t acc = 0;
-    while (i < n && (s.count == 0 || acc < target))
+    while (i < n && (s.count < min_units || acc < target))
     {
       const LzbUnit &x = u[i];
       /* keep the slice's arena windows tight: stop when a unit jumps far away from the window */
@@ -226,7 +228,21 @@ extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t pa
   const uint32_t model = model_bytes_for(units, n);
   const size_t slab = slab_bytes_for(model);
   std::vector<Slice> slices;
-  make_slices(units, n, slices);
+  {
+    uint32_t w = 1, ctas = 1, region = 0; int shared_model = 1;
+    lzb_launch_geometry(model, &w, &ctas, &region, &shared_model);
+    make_slices(units, n, (size_t)w * ctas, slices);
+    /* a short last slice would run alone on an almost empty GPU: merge it into its predecessor */
+    if (slices.size() >= 2 && slices.back().count < (size_t)w * ctas)
+    {
+      Slice tail = slices.back();
+      slices.pop_back();
+      Slice &p = slices.back();
+      p.count += tail.count;
+      p.src_lo = std::min(p.src_lo, tail.src_lo); p.src_hi = std::max(p.src_hi, tail.src_hi);
+      p.dst_lo = std::min(p.dst_lo, tail.dst_lo); p.dst_hi = std::max(p.dst_hi, tail.dst_hi);
+    }
+  }
 
   SRes ret = SZ_OK;
   std::vector<int> pending_slot(LZB_SLOTS, -1);          /* slice index in flight on each slot */

@@ -227,7 +227,7 @@ static SRes step(CLzmaDec *p, CLzma2Dec *l2, SizeT dicLimit, const Byte *src, Si
   }
   else
     *srcLen = 0;                                          /* nothing consumed: parked bytes stay parked */
-  *status = (ELzmaStatus)x.status;
+  *status = (ELzmaStatus)(x.status == LZB_ST_INHERIT ? LZMA_STATUS_NOT_SPECIFIED : x.status);
   return x.res;
 }
 

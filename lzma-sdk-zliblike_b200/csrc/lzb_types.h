@@ -78,6 +78,9 @@ typedef struct LzbResult
 #define LZB_SZ_ERROR_ARCHIVE 16
 #define LZB_SZ_ERROR_NO_ARCHIVE 17
 
+/* LZMA2 units only: the unit never assigned *status (only stored chunks / headers ran), so the caller's
+ * previous value stands -- the reference's *status is sticky across chunks (Lzma2Dec.c:175,282-283) */
+#define LZB_ST_INHERIT (-1)
 #define LZB_ST_NOT_SPECIFIED 0
 #define LZB_ST_FINISHED_WITH_MARK 1
 #define LZB_ST_NOT_FINISHED 2

@@ -74,7 +74,8 @@ class Emu:
         fill(u, R)
         out = np.zeros(max(cap, 1) + 64, np.uint8)
         r = decode_units(pad, out, u)[0]
-        return dict(res=int(r["res"]), status=int(r["status"]), dest_len=int(r["dst_done"]),
+        # LZB_ST_INHERIT (-1): the unit never assigned *status; a fresh call starts from NOT_SPECIFIED
+        return dict(res=int(r["res"]), status=max(int(r["status"]), 0), dest_len=int(r["dst_done"]),
                     src_len=int(r["src_used"]), out=out[3:3 + cap], check=int(r["check"]))
 
     def lzma_decode(self, packed, props, dest_cap, finish_mode=0):

@@ -90,7 +90,7 @@ class _EmuDecoder:
             src_len = used - prefix
         else:
             src_len = 0
-        return int(r["res"]), int(r["status"]), src_len
+        return int(r["res"]), max(int(r["status"]), 0), src_len      # -1 = LZB_ST_INHERIT -> NOT_SPECIFIED
 
     def to_buf(self, dptr, dl, sptr, sl, finish, st):
         """LzmaDec_DecodeToBuf / Lzma2Dec_DecodeToBuf (reference LzmaDec.c:840-878) over to_dic."""

@@ -44,7 +44,7 @@ def run_matrix(impl, want, streams2=True, heavy=False):
     rng = np.random.default_rng(31)
     for packed, props, n in lzma_streams():
         for ic, oc in CHUNKINGS:
-            if not heavy and n > 30000 and min(ic, oc) < 19:
+            if not heavy and n > 6000 and min(ic, oc) < 19:
                 continue
             for fm in (0, 1):
                 same(want.lzma_decode_tobuf(packed, props, n, ic, oc, fm), impl.lzma_decode_tobuf(packed, props, n, ic, oc, fm))

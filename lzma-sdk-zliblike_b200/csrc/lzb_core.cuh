@@ -139,7 +139,6 @@ struct UnitDecoder
   uint32_t range, code;
   uint32_t win;            /* upcoming input bytes, next byte in bits 31..24 */
   uint32_t win_left;       /* bytes still in `win` (1..4) */
-  uint32_t fetch;          /* unit-relative offset of the first byte NOT yet moved into `win` */
   uint32_t nextw;          /* raw little-endian word that follows `win` (prefetched) */
   const uint32_t *wbase;   /* `in` rounded down to a 4-byte boundary (pointer arithmetic keeps it a global pointer) */
   uint32_t in_skew;        /* in - wbase (0..3) */
@@ -166,7 +165,9 @@ struct UnitDecoder
   uint32_t held_out;       /* input bytes parked for the next call (CLzmaDec.tempBufSize) when starved */
 
   /* ---------------- input window ---------------- */
-  LZB_FN uint32_t in_pos() const { return fetch - win_left; }
+  /* `win` holds the next 1..4 packed bytes (next byte on top); `nextw` is the word after it, loaded one
+   * refill ahead; `widx` is the word index nextw came from.  Consumed position = 4*widx - skew - win_left. */
+  LZB_FN uint32_t in_pos() const { return (widx << 2) - in_skew - win_left; }
 
   LZB_FN uint32_t load_word(uint32_t i) const { return i < wcount ? wbase[i] : 0u; }
 
@@ -177,51 +178,95 @@ struct UnitDecoder
     widx = a >> 2;
     win = lzb_bswap(load_word(widx)) << (8 * sh);
     win_left = 4 - sh;
-    fetch = pos + win_left;
     widx += 1;
     nextw = load_word(widx);
   }
 
-  LZB_FN void rc_refill()
-  {
-    win = lzb_bswap(nextw);
-    win_left = 4;
-    fetch += 4;
-    widx += 1;
-    nextw = load_word(widx);
-  }
-
-  /* LzmaDec.c:17 */
+  /* LzmaDec.c:17.  The bit loop is issue/latency bound (profiles/), so the hot primitives are written as
+   * PTX with UNIFORM branches: all 32 lanes hold identical values, `bra.uni` tells ptxas so and spares
+   * the BSSY/BSYNC reconvergence pair a possibly-divergent `if` costs on every bit. */
   LZB_FN void rc_norm()
   {
+#ifdef LZB_EMU
     if (range < kTop)
     {
       range <<= 8;
       code = lzb_funnel_l8(win, code);
       win <<= 8;
-      if (--win_left == 0) rc_refill();
+      if (--win_left == 0)
+      {
+        win = lzb_bswap(nextw);
+        win_left = 4;
+        widx += 1;
+        nextw = load_word(widx);
+      }
     }
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pn, pr, pe;\n\t"
+        ".reg .u64 ad;\n\t"
+        "setp.ge.u32 pn, %0, 0x1000000;\n\t"
+        "@pn bra.uni LZB_NORM_DONE_%=;\n\t"
+        "shl.b32 %0, %0, 8;\n\t"
+        "shf.l.wrap.b32 %1, %2, %1, 8;\n\t"
+        "shl.b32 %2, %2, 8;\n\t"
+        "add.u32 %3, %3, -1;\n\t"
+        "setp.ne.u32 pr, %3, 0;\n\t"
+        "@pr bra.uni LZB_NORM_DONE_%=;\n\t"
+        "prmt.b32 %2, %5, 0, 0x0123;\n\t"
+        "mov.u32 %3, 4;\n\t"
+        "add.u32 %4, %4, 1;\n\t"
+        "mov.u32 %5, 0;\n\t"
+        "setp.ge.u32 pe, %4, %6;\n\t"
+        "@pe bra.uni LZB_NORM_DONE_%=;\n\t"
+        "mad.wide.u32 ad, %4, 4, %7;\n\t"
+        "ld.global.u32 %5, [ad];\n\t"
+        "LZB_NORM_DONE_%=:\n\t"
+        "}"
+        : "+r"(range), "+r"(code), "+r"(win), "+r"(win_left), "+r"(widx), "+r"(nextw)
+        : "r"(wcount), "l"(wbase)
+        : "memory");
+#endif
   }
 
-  /* LzmaDec.c:19-21 */
+  /* LzmaDec.c:19-21.  Select/predicate form, no branch on the decoded bit.  Probability update with
+   * one select:  bit 0: p + ((2048 - p) >> 5) == p - ((p - 2017) >>arith 5);  bit 1: p - ((p - 0) >>arith 5). */
   LZB_FN uint32_t rc_bit(uint16_t *p)
   {
-    /* select form (no branch on the decoded bit): every lane takes the same straight-line path.
-     * Probability update, both outcomes in one expression:
-     *   bit 0:  p + ((2048 - p) >> 5)  ==  p - ((p - 2017) >>arith 5)      (floor division of a negative)
-     *   bit 1:  p - (p >> 5)           ==  p - ((p -    0) >>arith 5)                                   */
     const uint32_t pr = *p;
     rc_norm();
+#ifdef LZB_EMU
     const uint32_t bound = (range >> 11) * pr;
     const bool one = code >= bound;
     const uint32_t rest = range - bound;
     range = one ? rest : bound;
     code = one ? code - bound : code;
-    /* (2048 - p) >> 5 == 64 - ((p + 31) >> 5), so with (A, B) = bit ? (0, 0) : (64, 31):
-     *   p' = p + A - ((p + B) >> 5)   -- unsigned throughout, one select feeds both constants */
-    const uint32_t ab = one ? 0u : ((64u << 16) | 31u);
-    *p = (uint16_t)(pr + (ab >> 16) - ((pr + (ab & 0xFFFFu)) >> 5));
+    const int32_t k = one ? 0 : 2017;
+    *p = (uint16_t)(pr - (uint32_t)(((int32_t)pr - k) >> 5));
     return one ? 1u : 0u;
+#else
+    uint32_t bit, np;
+    asm("{\n\t"
+        ".reg .pred q;\n\t"
+        ".reg .u32 b, t, k;\n\t"
+        "shr.u32 b, %0, 11;\n\t"
+        "mul.lo.u32 b, b, %4;\n\t"
+        "setp.ge.u32 q, %1, b;\n\t"
+        "sub.u32 t, %0, b;\n\t"
+        "selp.u32 %0, t, b, q;\n\t"
+        "@q sub.u32 %1, %1, b;\n\t"
+        "selp.u32 %2, 1, 0, q;\n\t"
+        "selp.u32 k, 0, 2017, q;\n\t"
+        "sub.u32 k, %4, k;\n\t"
+        "shr.s32 k, k, 5;\n\t"
+        "sub.u32 %3, %4, k;\n\t"
+        "}"
+        : "+r"(range), "+r"(code), "=r"(bit), "=r"(np)
+        : "r"(pr));
+    *p = (uint16_t)np;
+    return bit;
+#endif
   }
 
   /* LzmaDec.c:325-334, exact wrap-around arithmetic */
@@ -747,7 +792,7 @@ struct UnitDecoder
     probs = model;
     dic = out; dic_size = out_cap; dic_pos = 0; dic_commit = 0;
     dict_size = dict;
-    range = code = 0; win = 0; win_left = 4; fetch = 4; nextw = 0; widx = wcount;
+    range = code = 0; win = 0; win_left = 4; nextw = 0; widx = wcount;
     state = 0; rep0 = rep1 = rep2 = rep3 = 1;
     prev_byte = peek_byte = 0;
     reset_dic_state(true, true);                                                 /* LzmaDec_Init, :701-705 */

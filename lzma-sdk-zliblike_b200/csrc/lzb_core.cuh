@@ -148,7 +148,8 @@ struct UnitDecoder
   uint32_t in_len;
 
   /* model */
-  uint16_t *probs;
+  uint16_t *probs;         /* shared memory: fixed tables, pos-state tables, plain-literal trees (256/context) */
+  uint16_t *mprobs;        /* HBM (L2-resident slab): matched-literal trees (512/context), 16-byte aligned    */
   uint32_t lc, lp, lp_mask, pb, pb_mask;
 
   /* LZ state (CLzmaDec, LzmaDec.h:50-69) */
@@ -163,6 +164,7 @@ struct UnitDecoder
   uint32_t peek_byte;      /* dic[dicPos-rep0], valid while state >= 7 (matched literal) */
   bool want_rc_init, want_state_init;
   uint32_t held_out;       /* input bytes parked for the next call (CLzmaDec.tempBufSize) when starved */
+  bool probs_in_smem;      /* `probs` is a shared-memory address (the usual case): enables the ld/st.shared forms */
 
   /* ---------------- input window ---------------- */
   /* `win` holds the next 1..4 packed bytes (next byte on top); `nextw` is the word after it, loaded one
@@ -269,6 +271,57 @@ struct UnitDecoder
 #endif
   }
 
+  /* Plain literal, LzmaDec.c:174: eight steps down the context's 256-entry tree.  On the GPU the walk is
+   * kept in terms of the node's 32-bit shared-memory BYTE address A (node m of a tree at L: A = L + 2m):
+   * the child address is 2A + (bit ? 2 - L : -L), one select inside the bit step + one multiply-add, where
+   * index arithmetic on m needs four instructions.  80 % of all decoded bits are of this kind (profiles/). */
+  LZB_FN uint32_t literal_plain(uint16_t *lit)
+  {
+#ifdef LZB_EMU
+    uint32_t sym = 1;
+    for (int i = 0; i < 8; i++) sym = (sym << 1) | rc_bit(lit + sym);
+    return sym;
+#else
+    if (!probs_in_smem)
+    {
+      uint32_t sym = 1;
+#pragma unroll 1
+      for (int i = 0; i < 8; i++) sym = (sym << 1) | rc_bit(lit + sym);
+      return sym;
+    }
+    const uint32_t L = (uint32_t)__cvta_generic_to_shared(lit);
+    const uint32_t k0 = 0u - L, k1 = 2u - L;
+    uint32_t A = L + 2;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+      uint32_t pr, np, c;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=r"(pr) : "r"(A) : "memory");
+      rc_norm();
+      asm("{\n\t"
+          ".reg .pred q;\n\t"
+          ".reg .u32 b, t, k;\n\t"
+          "shr.u32 b, %0, 11;\n\t"
+          "mul.lo.u32 b, b, %4;\n\t"
+          "setp.ge.u32 q, %1, b;\n\t"
+          "sub.u32 t, %0, b;\n\t"
+          "selp.u32 %0, t, b, q;\n\t"
+          "@q sub.u32 %1, %1, b;\n\t"
+          "selp.u32 %2, %6, %5, q;\n\t"
+          "selp.u32 k, 0, 2017, q;\n\t"
+          "sub.u32 k, %4, k;\n\t"
+          "shr.s32 k, k, 5;\n\t"
+          "sub.u32 %3, %4, k;\n\t"
+          "}"
+          : "+r"(range), "+r"(code), "=r"(c), "=r"(np)
+          : "r"(pr), "r"(k0), "r"(k1));
+      asm volatile("st.shared.u16 [%0], %1;" : : "r"(A), "r"(np) : "memory");
+      A = A * 2 + c;
+    }
+    return (A - L) >> 1;
+#endif
+  }
+
   /* LzmaDec.c:325-334, exact wrap-around arithmetic */
   LZB_FN uint32_t rc_direct()
   {
@@ -316,14 +369,18 @@ struct UnitDecoder
   /* LzmaDec.c:707-717 */
   LZB_FN void init_models()
   {
-    const uint32_t n = lzb_num_probs(lc, lp, pb);
+    const uint32_t ns = lzb_smem_probs(lc, lp, pb), ng = lzb_gmem_probs(lc, lp);
     const uint32_t lane = lzb_lane();
 #ifdef LZB_EMU
-    for (uint32_t i = 0; i < n; i++) probs[i] = (uint16_t)kProbInit;
+    for (uint32_t i = 0; i < ns; i++) probs[i] = (uint16_t)kProbInit;
+    for (uint32_t i = 0; i < ng; i++) mprobs[i] = (uint16_t)kProbInit;
 #else
-    /* n is even; write two models per 32-bit store */
+    /* both counts are even; write two models per 32-bit store (the HBM part: 16 bytes per lane) */
     uint32_t *p32 = reinterpret_cast<uint32_t *>(probs);
-    for (uint32_t i = lane; i < (n >> 1); i += LZB_LANES) p32[i] = kProbInit | (kProbInit << 16);
+    for (uint32_t i = lane; i < (ns >> 1); i += LZB_LANES) p32[i] = kProbInit | (kProbInit << 16);
+    uint4 *g128 = reinterpret_cast<uint4 *>(mprobs);
+    const uint32_t v = kProbInit | (kProbInit << 16);
+    for (uint32_t i = lane; i < (ng >> 3); i += LZB_LANES) g128[i] = make_uint4(v, v, v, v);
 #endif
     (void)lane;
     lzb_syncwarp();
@@ -388,24 +445,28 @@ struct UnitDecoder
       if (rc_bit(P + oVar + (state << pb) + ps) == 0)
       {
         /* ---- literal, :161-196 ---- */
-        uint16_t *lit = P + oVar + (56u << pb) + 768u * (((total_pos & lp_mask) << lc) + (prev_byte >> (8 - lc)));
+        const uint32_t ctx = ((total_pos & lp_mask) << lc) + (prev_byte >> (8 - lc));
+        uint16_t *lit = P + oVar + (56u << pb) + (ctx << 8);       /* plain tree of this context (shared) */
         uint32_t sym = 1;
         if (state < 7)
         {
           state -= (state < 4) ? state : 3;
-#pragma unroll
-          for (int i = 0; i < 8; i++) sym = (sym << 1) | rc_bit(lit + sym);
+          sym = literal_plain(lit);
         }
         else
         {
+          /* matched literal (:176-192): while the decoded bits agree with the match byte the node comes
+           * from the context's matched trees (reference index 0x100 + mbit + sym -> HBM slab index
+           * mbit + sym); after the first disagreement the rest of the byte uses the plain tree. */
+          uint16_t *mlit = mprobs + (ctx << 9);
           uint32_t mb = peek_byte, offs = 0x100;
           state -= (state < 10) ? 3 : 6;
-#pragma unroll
+#pragma unroll 1
           for (int i = 0; i < 8; i++)
           {
             mb <<= 1;
             const uint32_t mbit = mb & offs;
-            const uint32_t b = rc_bit(lit + offs + mbit + sym);
+            const uint32_t b = rc_bit(offs ? mlit + mbit + sym : lit + sym);
             sym = (sym << 1) | b;
             offs &= b ? mbit : ~mbit;
           }
@@ -595,7 +656,7 @@ struct UnitDecoder
   };
 
   /* a free-standing (non-member, by-value) routine so that the decoder object stays in registers */
-  static LZB_NOINLINE int peek_symbol_impl(const uint16_t *P, const uint8_t *in, uint32_t range, uint32_t code,
+  static LZB_NOINLINE int peek_symbol_impl(const uint16_t *P, const uint16_t *M, const uint8_t *in, uint32_t range, uint32_t code,
                                            uint32_t at, uint32_t avail, uint32_t state, uint32_t total_pos,
                                            uint32_t lc, uint32_t lp_mask, uint32_t pb, uint32_t prev_byte,
                                            uint32_t peek_byte)
@@ -606,7 +667,9 @@ struct UnitDecoder
     int kind;
     if (k.bit(P + oVar + (state << pb) + ps) == 0)
     {
-      const uint16_t *lit = P + oVar + (56u << pb) + 768u * (((total_pos & lp_mask) << lc) + (prev_byte >> (8 - lc)));
+      const uint32_t ctx = ((total_pos & lp_mask) << lc) + (prev_byte >> (8 - lc));
+      const uint16_t *lit = P + oVar + (56u << pb) + (ctx << 8);
+      const uint16_t *mlit = M + (ctx << 9);
       uint32_t sym = 1;
       if (state < 7)
       {
@@ -619,7 +682,7 @@ struct UnitDecoder
         {
           mb <<= 1;
           const uint32_t mbit = mb & offs;
-          const uint32_t b = k.bit(lit + offs + mbit + sym);
+          const uint32_t b = k.bit(offs ? mlit + mbit + sym : lit + sym);
           sym = (sym << 1) | b;
           offs &= b ? mbit : ~mbit;
         }
@@ -679,7 +742,7 @@ struct UnitDecoder
 
   LZB_FN int peek_symbol(uint32_t at, uint32_t avail) const
   {
-    return peek_symbol_impl(probs, in, range, code, at, avail, state, total_pos, lc, lp_mask, pb, prev_byte, peek_byte);
+    return peek_symbol_impl(probs, mprobs, in, range, code, at, avail, state, total_pos, lc, lp_mask, pb, prev_byte, peek_byte);
   }
 
   /* LzmaDec.c:719-838 for an input that is completely present (the `tempBuf` continuation branch,
@@ -751,10 +814,13 @@ struct UnitDecoder
     set_props(s->lc, s->lp, s->pb);
     if (!want_state_init)
     {
-      const uint32_t n32 = lzb_num_probs(lc, lp, pb) >> 1;
+      /* blob behind the header: shared-memory part, then the matched-literal part */
+      const uint32_t ns32 = lzb_smem_probs(lc, lp, pb) >> 1, ng32 = lzb_gmem_probs(lc, lp) >> 1;
       const uint32_t *g = reinterpret_cast<const uint32_t *>(s + 1);
       uint32_t *p32 = reinterpret_cast<uint32_t *>(probs);
-      for (uint32_t i = lzb_lane(); i < n32; i += LZB_LANES) p32[i] = g[i];
+      uint32_t *m32 = reinterpret_cast<uint32_t *>(mprobs);
+      for (uint32_t i = lzb_lane(); i < ns32; i += LZB_LANES) p32[i] = g[i];
+      for (uint32_t i = lzb_lane(); i < ng32; i += LZB_LANES) m32[i] = g[ns32 + i];
       lzb_syncwarp();
     }
   }
@@ -764,10 +830,12 @@ struct UnitDecoder
     lzb_syncwarp();
     if (!want_state_init)
     {
-      const uint32_t n32 = lzb_num_probs(lc, lp, pb) >> 1;
+      const uint32_t ns32 = lzb_smem_probs(lc, lp, pb) >> 1, ng32 = lzb_gmem_probs(lc, lp) >> 1;
       uint32_t *g = reinterpret_cast<uint32_t *>(s + 1);
       const uint32_t *p32 = reinterpret_cast<const uint32_t *>(probs);
-      for (uint32_t i = lzb_lane(); i < n32; i += LZB_LANES) g[i] = p32[i];
+      const uint32_t *m32 = reinterpret_cast<const uint32_t *>(mprobs);
+      for (uint32_t i = lzb_lane(); i < ns32; i += LZB_LANES) g[i] = p32[i];
+      for (uint32_t i = lzb_lane(); i < ng32; i += LZB_LANES) g[ns32 + i] = m32[i];
     }
     if (lzb_lane() == 0)
     {
@@ -782,9 +850,11 @@ struct UnitDecoder
   }
 
   LZB_FN void begin(const uint8_t *packed, uint32_t packed_len, uint8_t *out, uint32_t out_cap,
-                    uint32_t dict, uint16_t *model)
+                    uint32_t dict, uint16_t *model, uint16_t *matched_model, bool model_in_smem = false)
   {
     held_out = 0;
+    mprobs = matched_model;
+    probs_in_smem = model_in_smem;
     in = packed; in_len = packed_len;
     in_skew = (uint32_t)((uintptr_t)packed & 3);
     wbase = reinterpret_cast<const uint32_t *>(packed - in_skew);

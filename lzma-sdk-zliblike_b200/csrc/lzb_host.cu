@@ -143,7 +143,17 @@ bool lzb_slot_reserve(LzbContext *c, LzbSlot &s, size_t packed, size_t out, size
 
 /* probability-model bytes needed by a set of units (upper bound: monotone in lc+lp and pb).
  * LZMA2 units carry the walker's maxima in lc (= max lc+lp) and pb. */
-static uint32_t model_bytes_for(const LzbUnit *u, size_t n)
+struct ModelBytes { uint32_t smem, gmem; };
+
+static ModelBytes model_bytes_of(unsigned lclp, unsigned pb)
+{
+  ModelBytes m;
+  m.smem = lzb_smem_probs(lclp, 0, pb) * 2u;     /* fixed + pos-state tables + plain-literal trees */
+  m.gmem = lzb_gmem_probs(lclp, 0) * 2u;         /* matched-literal trees                          */
+  return m;
+}
+
+static ModelBytes model_bytes_for(const LzbUnit *u, size_t n)
 {
   unsigned lclp = 0, pb = 0;
   for (size_t i = 0; i < n; i++)
@@ -152,14 +162,14 @@ static uint32_t model_bytes_for(const LzbUnit *u, size_t n)
     if (a > lclp) lclp = a;
     if (u[i].pb > pb) pb = u[i].pb;
   }
-  return lzb_num_probs(lclp, 0, pb) * 2u;
+  return model_bytes_of(lclp, pb);
 }
 
-static size_t slab_bytes_for(uint32_t model_bytes)
+static size_t slab_bytes_for(ModelBytes m)
 {
-  uint32_t w, ctas, region; int shared_model;
-  if (lzb_launch_geometry(model_bytes, &w, &ctas, &region, &shared_model) != 0) return 0;
-  return shared_model ? 0 : (size_t)w * ctas * region;
+  LzbGeometry g;
+  if (lzb_launch_geometry(m.smem, m.gmem, &g) != 0) return 0;
+  return g.slab_bytes;
 }
 
 /* ------------------------------------------------------------------ device-resident batch ---- */
@@ -170,12 +180,12 @@ extern "C" SRes Lzb_DecodeUnitsDevice(LzbContext *c, const Byte *d_packed, Byte 
   if (n > 0xFFFFFFFFull) return SZ_ERROR_PARAM;
   std::lock_guard<std::mutex> g(c->mu);
   if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
-  const uint32_t model = lzb_num_probs(maxLcLp, 0, maxPb) * 2u;
+  const ModelBytes model = model_bytes_of(maxLcLp, maxPb);
   const size_t slab = slab_bytes_for(model);
   if (slab && !grow(c->d_dev_slab, c->dev_slab_cap, slab, "cudaMalloc model slab")) return SZ_ERROR_MEM;
   cudaStream_t st = (cudaStream_t)stream;        /* NULL = the CUDA default stream, as everywhere in CUDA */
   uint32_t *ticket = c->d_dev_tickets + (c->dev_seq++ % 64);
-  int rc = lzb_launch_decode(d_packed, d_out, d_units, d_results, (uint32_t)n, ticket, model, c->d_dev_slab, st);
+  int rc = lzb_launch_decode(d_packed, d_out, d_units, d_results, (uint32_t)n, ticket, model.smem, model.gmem, c->d_dev_slab, st);
   if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
   return SZ_OK;
 }
@@ -225,12 +235,14 @@ extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t pa
   std::lock_guard<std::mutex> g(c->mu);
   if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
 
-  const uint32_t model = model_bytes_for(units, n);
+  const ModelBytes model = model_bytes_for(units, n);
   const size_t slab = slab_bytes_for(model);
   std::vector<Slice> slices;
   {
-    uint32_t w = 1, ctas = 1, region = 0; int shared_model = 1;
-    lzb_launch_geometry(model, &w, &ctas, &region, &shared_model);
+    LzbGeometry geo;
+    geo.warps_per_cta = 1; geo.ctas = 1;
+    lzb_launch_geometry(model.smem, model.gmem, &geo);
+    const uint32_t w = geo.warps_per_cta, ctas = geo.ctas;
     make_slices(units, n, (size_t)w * ctas, slices);
     /* a short last slice would run alone on an almost empty GPU: merge it into its predecessor */
     if (slices.size() >= 2 && slices.back().count < (size_t)w * ctas)
@@ -275,7 +287,7 @@ extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t pa
     bool ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_packed, packed + sl.src_lo, pbytes, cudaMemcpyHostToDevice, s.stream), "H2D packed") &&
               lzb_cuda_ok(cudaMemcpyAsync(s.d_units, s.h_units, sl.count * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D units");
     if (!ok) { ret = SZ_ERROR_FAIL; break; }
-    int rc = lzb_launch_decode(s.d_packed, s.d_out, s.d_units, s.d_results, (uint32_t)sl.count, s.d_ticket, model, s.d_slab, s.stream);
+    int rc = lzb_launch_decode(s.d_packed, s.d_out, s.d_units, s.d_results, (uint32_t)sl.count, s.d_ticket, model.smem, model.gmem, s.d_slab, s.stream);
     if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); ret = SZ_ERROR_FAIL; break; }
     /* D2H: one copy per maximal run of units whose outputs tile the arena (never touch the gaps) */
     size_t j = 0;
@@ -304,10 +316,10 @@ SRes lzb_run_resident(LzbContext *c, const uint8_t *d_packed, uint8_t *d_out, co
   std::lock_guard<std::mutex> g(c->mu);
   if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
   LzbSlot &s = c->slot[0];
-  const uint32_t model = model_bytes_for(units, n);
+  const ModelBytes model = model_bytes_for(units, n);
   if (!lzb_slot_reserve(c, s, 0, 0, n, slab_bytes_for(model))) return SZ_ERROR_MEM;
   if (!lzb_cuda_ok(cudaMemcpyAsync(s.d_units, units, n * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D units")) return SZ_ERROR_FAIL;
-  int rc = lzb_launch_decode(d_packed, d_out, s.d_units, s.d_results, (uint32_t)n, s.d_ticket, model, s.d_slab, s.stream);
+  int rc = lzb_launch_decode(d_packed, d_out, s.d_units, s.d_results, (uint32_t)n, s.d_ticket, model.smem, model.gmem, s.d_slab, s.stream);
   if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
   if (!lzb_cuda_ok(cudaMemcpyAsync(results, s.d_results, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results") ||
       !lzb_cuda_ok(cudaStreamSynchronize(s.stream), "decode kernel")) return SZ_ERROR_FAIL;

@@ -3,26 +3,36 @@
 #define LZB_KERNELS_H
 
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "lzb_types.h"
 
-#define LZB_MAX_WARPS_PER_CTA 16
+#define LZB_MAX_WARPS_PER_CTA 32
+#define LZB_DEFAULT_WARPS_PER_CTA 24
 #define LZB_MAX_SHARED_MODEL_BYTES (56u * 1024u)
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-/* Residency the decode kernel will use for a given probability-model size (bytes). */
-int lzb_launch_geometry(uint32_t model_bytes, uint32_t *warps_per_cta, uint32_t *ctas, uint32_t *region_bytes,
-                        int *shared_model);
+typedef struct LzbGeometry
+{
+  uint32_t warps_per_cta;   /* resident units per SM                                   */
+  uint32_t ctas;            /* one per SM                                              */
+  uint32_t region_bytes;    /* shared-memory bytes per warp (model / post-pass scratch) */
+  uint32_t slab_stride;     /* HBM slab bytes per warp (matched-literal trees, or the whole model) */
+  int shared_model;
+  size_t slab_bytes;        /* slab the caller must provide: ctas * warps_per_cta * slab_stride */
+} LzbGeometry;
 
-/* Decode n_units units.  d_ticket: one uint32 of device scratch.  d_model_slab: only needed when the
- * model does not fit shared memory (ctas * warps_per_cta * region_bytes bytes), else NULL. */
+/* Residency the decode kernel will use for a model of the given shared / HBM part sizes (bytes). */
+int lzb_launch_geometry(uint32_t smem_model_bytes, uint32_t gmem_model_bytes, LzbGeometry *g);
+
+/* Decode n_units units.  d_ticket: one uint32 of device scratch.  d_model_slab: g.slab_bytes bytes. */
 int lzb_launch_decode(const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *d_units, LzbResult *d_results,
-                      uint32_t n_units, uint32_t *d_ticket, uint32_t model_bytes, uint8_t *d_model_slab,
-                      cudaStream_t stream);
+                      uint32_t n_units, uint32_t *d_ticket, uint32_t smem_model_bytes, uint32_t gmem_model_bytes,
+                      uint8_t *d_model_slab, cudaStream_t stream);
 
 /* Filter/check only, over bytes already in device memory (dst_off/dst_cap/filter/check of each unit). */
 int lzb_launch_post_only(uint8_t *d_data, const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units,

@@ -19,7 +19,8 @@
 
 namespace lzb {
 
-constexpr uint32_t kPostScratchBytes = 8192;
+constexpr uint32_t kPostScratchBytes = 8192;                 /* Delta column sums: 256 x 32 bytes   */
+constexpr uint32_t kPostSmemBytes = 2048;                    /* CRC-64 table: 256 x 8 bytes         */
 constexpr uint32_t kPoly32 = 0xEDB88320u;                    /* 7zCrc.c:7  */
 constexpr uint64_t kPoly64 = 0xC96C5795D7870F42ull;          /* XzCrc64.c:6 */
 
@@ -259,7 +260,10 @@ LZB_FN uint64_t crc64_warp(const uint8_t *data, uint32_t size, uint64_t *table /
 }
 
 /* filter -> check -> verdict, for one decoded unit.  `scratch` = the warp's dead probability region. */
-LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t *scratch)
+/* `scratch`     : >= kPostSmemBytes of the warp's (dead) shared-memory model region -- CRC table.
+ * `big_scratch` : >= kPostScratchBytes, the warp's (dead) matched-literal slab slice in HBM/L2 -- Delta
+ *                 column sums (up to 256 x 32 bytes; Delta blocks are rare, L2 latency is acceptable). */
+LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t *scratch, uint8_t *big_scratch)
 {
   if (r.res != LZB_SZ_OK) return;
   const uint32_t n = r.dst_done;
@@ -270,7 +274,7 @@ LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t 
     const uint32_t done = x86_convert_warp(data, n, u.filter_param, (u.flags & 2) != 0, st);
     if (u.flags & 4) { r.src_used = done; r.status = (int32_t)st; }   /* stand-alone call: report them */
   }
-  else if (u.filter == LZB_FILTER_DELTA) delta_decode_warp(data, n, u.filter_param, scratch);
+  else if (u.filter == LZB_FILTER_DELTA) delta_decode_warp(data, n, u.filter_param, big_scratch);
   if (u.check == LZB_CHECK_CRC32) r.check = crc32_warp(data, n, reinterpret_cast<uint32_t *>(scratch));
   else if (u.check == LZB_CHECK_CRC64) r.check = crc64_warp(data, n, reinterpret_cast<uint64_t *>(scratch));
   if ((u.flags & LZB_UNIT_VERIFY) && u.check != LZB_CHECK_NONE && r.check != u.expect) r.res = LZB_SZ_ERROR_CRC;

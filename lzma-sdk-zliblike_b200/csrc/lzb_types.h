@@ -95,6 +95,24 @@ static inline uint32_t lzb_num_probs(unsigned lc, unsigned lp, unsigned pb)
 {
   return 950u + (56u << pb) + (768u << (lc + lp));
 }
+/* The model is kept in two places (lzb_core.cuh): everything a plain symbol touches -- 950 fixed +
+ * pos-state tables + the 256-entry plain-literal tree of every context -- in shared memory, and the
+ * 512-entry "matched literal" trees (used only for the literal right after a match) in an L2-resident
+ * slab in HBM.  lzb_num_probs == lzb_smem_probs + lzb_gmem_probs. */
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline uint32_t lzb_smem_probs(unsigned lc, unsigned lp, unsigned pb)
+{
+  return 950u + (56u << pb) + (256u << (lc + lp));
+}
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline uint32_t lzb_gmem_probs(unsigned lc, unsigned lp)
+{
+  return 512u << (lc + lp);
+}
 
 #ifdef __cplusplus
 }

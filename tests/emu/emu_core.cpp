@@ -22,7 +22,7 @@ extern "C" int emu_post_units(uint8_t *data, const LzbUnit *units, LzbResult *re
     const LzbUnit &u = units[i];
     LzbResult r;
     r.res = LZB_SZ_OK; r.status = LZB_ST_NOT_SPECIFIED; r.src_used = 0; r.dst_done = u.dst_cap; r.check = 0;
-    lzb::post_process(u, r, data + u.dst_off, scratch.data());
+    lzb::post_process(u, r, data + u.dst_off, scratch.data(), scratch.data());
     results[i] = r;
   }
   return 0;
@@ -31,21 +31,24 @@ extern "C" int emu_post_units(uint8_t *data, const LzbUnit *units, LzbResult *re
 extern "C" int emu_decode_units(const uint8_t *packed, uint8_t *out, const LzbUnit *units, LzbResult *results,
                                 uint32_t n)
 {
-  std::vector<uint16_t> probs;
-  std::vector<uint8_t> scratch(lzb::kPostScratchBytes);
+  std::vector<uint16_t> probs, matched;
   for (uint32_t i = 0; i < n; i++)
   {
     const LzbUnit &u = units[i];
     LzbResult r;
-    uint32_t np = u.codec == LZB_CODEC_LZMA2 ? lzb_num_probs(4, 0, 4) : lzb_num_probs(u.lc, u.lp, u.pb);
-    if (np * 2 < lzb::kPostScratchBytes) np = lzb::kPostScratchBytes / 2;
-    probs.assign(np, 0xDEAD);
+    const bool l2 = u.codec == LZB_CODEC_LZMA2;
+    uint32_t ns = l2 ? lzb_smem_probs(4, 0, 4) : lzb_smem_probs(u.lc, u.lp, u.pb);
+    uint32_t ng = l2 ? lzb_gmem_probs(4, 0) : lzb_gmem_probs(u.lc, u.lp);
+    if (ns * 2 < lzb::kPostSmemBytes) ns = lzb::kPostSmemBytes / 2;
+    if (ng * 2 < lzb::kPostScratchBytes) ng = lzb::kPostScratchBytes / 2;
+    probs.assign(ns, 0xDEAD);       /* poison: every model entry must be initialised by the decoder */
+    matched.assign(ng, 0xDEAD);
     lzb::UnitDecoder d;
     const bool stateful = (u.flags & LZB_UNIT_STATEFUL) != 0;
     d.begin(packed + u.src_off, u.src_len, out + u.dst_off, stateful ? u.filter_param : u.dst_cap, u.dict_size,
-            probs.data());
+            probs.data(), matched.data());
     lzb::decode_unit(d, u, r, stateful ? reinterpret_cast<LzbStreamState *>((uintptr_t)u.expect) : nullptr);
-    if (!stateful) lzb::post_process(u, r, out + u.dst_off, (uint8_t *)probs.data());
+    if (!stateful) lzb::post_process(u, r, out + u.dst_off, (uint8_t *)probs.data(), (uint8_t *)matched.data());
     results[i] = r;
   }
   return 0;

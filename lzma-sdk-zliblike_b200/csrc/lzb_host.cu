@@ -240,11 +240,11 @@ extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t pa
   std::vector<Slice> slices;
   {
     LzbGeometry geo;
-    geo.warps_per_cta = 1; geo.ctas = 1;
+    geo.warps_per_cta = 1; geo.units_per_cta = 1; geo.ctas = 1;
     lzb_launch_geometry(model.smem, model.gmem, &geo);
     /* every slice kernel ends with a tail of about one unit time during which the SMs drain (CTAs are
      * persistent); four waves per slice keep that under ~10 % while copies still overlap the kernels */
-    const uint32_t w = geo.warps_per_cta * 4, ctas = geo.ctas;
+    const uint32_t w = geo.units_per_cta * 4, ctas = geo.ctas;
     make_slices(units, n, (size_t)w * ctas, slices);
     /* a short last slice would run alone on an almost empty GPU: merge it into its predecessor */
     if (slices.size() >= 2 && slices.back().count < (size_t)w * ctas)

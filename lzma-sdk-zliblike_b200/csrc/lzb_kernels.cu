@@ -1,17 +1,16 @@
 /* lzb_kernels.cu -- sm_100a kernels and their launchers.
  *
- *   lzb_decode_units_kernel : persistent grid (one CTA per SM), every warp pulls the next unit from a
- *                             global ticket, decodes it (LZMA / LZMA2), applies the unit's post-filter
- *                             and check in the same launch and writes one LzbResult.
+ *   lzb_decode_units_kernel<shared model, G> : persistent grid (one CTA per SM).  Every warp carries
+ *       K = 32 / G units (G lanes each) and runs ONE loop in which each unit decodes one symbol per trip
+ *       (lzb_core.cuh); a group that finishes its unit pulls the next one from a global ticket, applies the
+ *       unit's post-filter and check and writes one LzbResult.
  *
- * Residency.  The bit loop is bound by issue slots and dependent-issue latency (profiles/), so what it
- * needs is resident warps per scheduler, and two things cap them: shared memory for the models and the
- * 64 K-entry register file (all 32 lanes of a warp carry the same decoder state).  Hence:
- *   - only the part of the model a plain symbol touches lives in shared memory (6,448 B at lc3/lp0/pb2);
- *     the matched-literal trees (8 KiB, touched once per match) live in an L2-resident HBM slab;
- *   - the kernel is built for kMaxWarps in {16, 24, 32} resident warps per SM with __launch_bounds__
- *     (kMaxWarps*32, 1), i.e. <= 128 / 80 / 64 registers per thread; the launcher picks the largest
- *     variant the shared-memory model allows (LZB_WARPS overrides, for measurements).
+ * Residency.  The bit loop is a serial dependency chain: throughput comes from resident units, and a warp
+ * instruction that serves K units at once costs one issue slot (profiles/r01_c_residency.md).  Two things
+ * cap the units per SM: shared memory for the models and the register file.  Only the part of the model a
+ * plain symbol touches lives in shared memory (6,448 B at lc3/lp0/pb2 -> 36 fit); the matched-literal trees
+ * (8 KiB, touched once per match) live in an L2-resident HBM slab.  With K units
+ * per warp only units/K warps need registers: the default is G = 16, 18 warps, 36 units per SM.
  * Models whose shared part exceeds 56 KiB (raw LZMA with lc+lp >= 6) live entirely in the slab.
  */
 #include <cuda_runtime.h>
@@ -24,37 +23,72 @@
 
 namespace lzb {
 
-template <bool kSharedModel, int kMaxWarps>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+/* warps per CTA a variant is compiled for (register budget = 65536 / (32 * warps), warps rounded up to a
+ * multiple of four): G = 32: 16 warps (128 registers), G = 16: 18 warps (96; a bound of 20 gives the same
+ * budget but a slower schedule: 7.17 vs 7.68 GB/s), G <= 8: 8 warps */
+constexpr uint32_t max_warps_for(uint32_t G) { return G == 32 ? 16u : (G == 16 ? 18u : 8u); }
+
+template <bool kSharedModel, uint32_t G>
+__global__ void __launch_bounds__(max_warps_for(G) * 32, 1)
 lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict__ out,
                         const LzbUnit *__restrict__ units, LzbResult *__restrict__ results, uint32_t n_units,
                         uint32_t *ticket, uint32_t region_bytes, uint32_t slab_stride, uint8_t *model_slab)
 {
   extern __shared__ __align__(16) uint8_t lzb_smem[];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  const uint32_t warps_per_cta = blockDim.x >> 5;
-  uint8_t *slab = model_slab + ((size_t)blockIdx.x * warps_per_cta + warp) * slab_stride;
-  /* shared model: region in shared memory, matched-literal trees at the start of the warp's slab slice;
+  typedef Group<G> Grp;
+  constexpr uint32_t K = 32 / G;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t grp = warp * K + ((threadIdx.x & 31u) / G);               /* group index inside the CTA */
+  const uint32_t groups_per_cta = (blockDim.x >> 5) * K;
+  uint8_t *slab = model_slab + ((size_t)blockIdx.x * groups_per_cta + grp) * slab_stride;
+  /* shared model: region in shared memory, matched-literal trees at the start of the group's slab slice;
    * global model: both in the slab slice (region first) */
-  uint8_t *region = kSharedModel ? lzb_smem + (size_t)warp * region_bytes : slab;
+  uint8_t *region = kSharedModel ? lzb_smem + (size_t)grp * region_bytes : slab;
   uint16_t *matched = reinterpret_cast<uint16_t *>(kSharedModel ? slab : slab + region_bytes);
+
+  UnitDecoderT<G> d;
+  LzbUnit u;
+  uint32_t ui = 0;
+  uint8_t *dst = out;
+  d.st = S_FETCH;
   for (;;)
   {
-    uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(ticket, 1u);
-    i = __shfl_sync(0xffffffffu, i, 0);
-    if (i >= n_units) break;
-    const LzbUnit u = units[i];
-    UnitDecoder d;
-    LzbResult r;
-    uint8_t *dst = out + u.dst_off;
-    const bool stateful = (u.flags & LZB_UNIT_STATEFUL) != 0;
-    d.begin(packed + u.src_off, u.src_len, dst, stateful ? u.filter_param : u.dst_cap, u.dict_size,
-            reinterpret_cast<uint16_t *>(region), matched, kSharedModel);
-    decode_unit(d, u, r, stateful ? reinterpret_cast<LzbStreamState *>(u.expect) : nullptr);
-    if (!stateful) post_process(u, r, dst, region, reinterpret_cast<uint8_t *>(matched));
-    if (lane == 0) results[i] = r;
-    __syncwarp();
+    if (d.st == S_FETCH)
+    {
+      uint32_t i = 0;
+      if (Grp::lane() == 0) i = atomicAdd(ticket, 1u);
+      i = Grp::bcast(i, 0);
+      if (i >= n_units) d.st = S_EXIT;
+      else
+      {
+        ui = i;
+        u = units[i];
+        dst = out + u.dst_off;
+        const bool stateful = (u.flags & LZB_UNIT_STATEFUL) != 0;
+        d.begin(packed + u.src_off, u.src_len, dst, stateful ? u.filter_param : u.dst_cap, u.dict_size,
+                reinterpret_cast<uint16_t *>(region), matched, kSharedModel);
+        d.start_unit(u, stateful ? reinterpret_cast<LzbStreamState *>(u.expect) : nullptr);
+      }
+    }
+    if (d.st != S_RUN && d.st != S_EXIT)
+    {
+      d.advance();
+      if (d.st == S_UNIT_END)
+      {
+        LzbResult r;
+        d.finish_unit(r);
+        if (!(u.flags & LZB_UNIT_STATEFUL)) post_process<G>(u, r, dst, region, reinterpret_cast<uint8_t *>(matched));
+        if (Grp::lane() == 0) results[ui] = r;
+        Grp::sync();
+        d.st = S_FETCH;
+      }
+    }
+    if (__all_sync(0xffffffffu, d.st == S_EXIT)) break;
+    /* hot loop: one symbol per unit and trip, until some unit of the warp needs the driver again */
+    do
+    {
+      if (d.st == S_RUN) d.step();
+    } while (!__any_sync(0xffffffffu, d.st != S_RUN && d.st != S_EXIT));
   }
 }
 
@@ -71,7 +105,7 @@ lzb_post_only_kernel(uint8_t *__restrict__ data, const LzbUnit *__restrict__ uni
   const LzbUnit u = units[i];
   LzbResult r;
   r.res = LZB_SZ_OK; r.status = LZB_ST_NOT_SPECIFIED; r.src_used = 0; r.dst_done = u.dst_cap; r.check = 0;
-  post_process(u, r, data + u.dst_off, scratch[warp], scratch[warp]);
+  post_process<32>(u, r, data + u.dst_off, scratch[warp], scratch[warp]);
   if (lane == 0) results[i] = r;
 }
 
@@ -96,6 +130,12 @@ static cudaError_t query_device()
   return cudaSuccess;
 }
 
+static uint32_t env_u32(const char *name, uint32_t dflt)
+{
+  const char *v = getenv(name);
+  return (v && atoi(v) > 0) ? (uint32_t)atoi(v) : dflt;
+}
+
 extern "C" int lzb_launch_geometry(uint32_t smem_model_bytes, uint32_t gmem_model_bytes, LzbGeometry *g)
 {
   cudaError_t e = query_device();
@@ -107,44 +147,54 @@ extern "C" int lzb_launch_geometry(uint32_t smem_model_bytes, uint32_t gmem_mode
   gpart = (gpart + 15u) & ~15u;
   g->region_bytes = region;
   g->ctas = (uint32_t)g_dev_sms;
-  /* measured on B200 (profiles/r01_c_residency.md): 16 / 24 / 32 warps per SM = 5.27 / 5.82 / 5.68 GB/s on the
-   * 64 KiB raw-LZMA batch; 24 (80 registers, no hot-loop spills) is the default, LZB_WARPS overrides */
-  uint32_t want = LZB_DEFAULT_WARPS_PER_CTA;
-  const char *ov = getenv("LZB_WARPS");
-  if (ov && atoi(ov) > 0) want = (uint32_t)atoi(ov);
+  /* lanes per unit (LZB_GROUP = 32, 16, 8 or 4) and units per SM (LZB_UNITS), both overridable for
+   * measurements; defaults from profiles/r01_c_residency.md */
+  uint32_t G = env_u32("LZB_GROUP", LZB_DEFAULT_GROUP);
+  if (G != 32 && G != 16 && G != 8 && G != 4) G = LZB_DEFAULT_GROUP;
+  const uint32_t K = 32 / G;
+  uint32_t want_units = env_u32("LZB_UNITS", LZB_DEFAULT_UNITS_PER_SM);
   if (region <= LZB_MAX_SHARED_MODEL_BYTES)
   {
-    uint32_t w = (uint32_t)(g_dev_smem_optin / region);
-    if (w > want) w = want;
-    if (w > LZB_MAX_WARPS_PER_CTA) w = LZB_MAX_WARPS_PER_CTA;
-    if (w < 1) w = 1;
-    g->warps_per_cta = w;
+    uint32_t units = (uint32_t)(g_dev_smem_optin / region);
+    if (units > want_units) units = want_units;
+    uint32_t warps = units / K;
+    if (warps > lzb::max_warps_for(G)) warps = lzb::max_warps_for(G);
+    /* a model so large that fewer than K fit: fall back to one unit per warp */
+    if (warps < 1)
+    {
+      G = 32;
+      warps = units < 1 ? 1 : (units > lzb::max_warps_for(32) ? lzb::max_warps_for(32) : units);
+    }
+    g->warps_per_cta = warps;
     g->shared_model = 1;
     g->slab_stride = gpart;
   }
   else
   {
+    G = 32;
     g->warps_per_cta = 8;
     g->shared_model = 0;
     g->slab_stride = region + gpart;
   }
-  g->slab_bytes = (size_t)g->slab_stride * g->warps_per_cta * g->ctas;
+  g->group = G;
+  g->units_per_cta = g->warps_per_cta * (32 / G);
+  g->slab_bytes = (size_t)g->slab_stride * g->units_per_cta * g->ctas;
   return 0;
 }
 
-template <bool kShared, int kMaxWarps>
+template <bool kShared, uint32_t G>
 static cudaError_t launch_variant(const LzbGeometry &g, uint32_t ctas, const uint8_t *d_packed, uint8_t *d_out,
                                   const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units, uint32_t *d_ticket,
                                   uint8_t *d_slab, cudaStream_t stream)
 {
-  const size_t smem = kShared ? (size_t)g.warps_per_cta * g.region_bytes : 0;
+  const size_t smem = kShared ? (size_t)g.units_per_cta * g.region_bytes : 0;
   if (kShared)
   {
-    cudaError_t e = cudaFuncSetAttribute(lzb::lzb_decode_units_kernel<kShared, kMaxWarps>,
+    cudaError_t e = cudaFuncSetAttribute(lzb::lzb_decode_units_kernel<kShared, G>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  lzb::lzb_decode_units_kernel<kShared, kMaxWarps><<<ctas, g.warps_per_cta * 32, smem, stream>>>(
+  lzb::lzb_decode_units_kernel<kShared, G><<<ctas, g.warps_per_cta * 32, smem, stream>>>(
       d_packed, d_out, d_units, d_results, n_units, d_ticket, g.region_bytes, g.slab_stride, d_slab);
   return cudaGetLastError();
 }
@@ -159,19 +209,29 @@ extern "C" int lzb_launch_decode(const uint8_t *d_packed, uint8_t *d_out, const 
   if (rc) return rc;
   if (n_units == 0) return 0;
   if (!d_model_slab) return (int)cudaErrorInvalidValue;
+  /* Few units (large LZMA2 groups, xz blocks): when every unit can have a warp of its own in one wave,
+   * sharing warps only serialises them.  The slab is sized for the default geometry, which is the larger. */
+  if (g.shared_model && g.group < 32 && !getenv("LZB_GROUP"))
+  {
+    const uint32_t w32 = g.units_per_cta < lzb::max_warps_for(32) ? g.units_per_cta : lzb::max_warps_for(32);
+    if (n_units <= g.ctas * w32)
+    {
+      g.group = 32;
+      g.warps_per_cta = w32;
+      g.units_per_cta = w32;
+    }
+  }
   uint32_t ctas = g.ctas;
-  if ((uint64_t)ctas * g.warps_per_cta > n_units) ctas = (n_units + g.warps_per_cta - 1) / g.warps_per_cta;
+  if ((uint64_t)ctas * g.units_per_cta > n_units) ctas = (n_units + g.units_per_cta - 1) / g.units_per_cta;
   cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return (int)e;
-  const uint32_t w = g.warps_per_cta;
-  if (!g.shared_model)
-    e = launch_variant<false, 16>(g, ctas, d_packed, d_out, d_units, d_results, n_units, d_ticket, d_model_slab, stream);
-  else if (w <= 16)
-    e = launch_variant<true, 16>(g, ctas, d_packed, d_out, d_units, d_results, n_units, d_ticket, d_model_slab, stream);
-  else if (w <= 24)
-    e = launch_variant<true, 24>(g, ctas, d_packed, d_out, d_units, d_results, n_units, d_ticket, d_model_slab, stream);
-  else
-    e = launch_variant<true, 32>(g, ctas, d_packed, d_out, d_units, d_results, n_units, d_ticket, d_model_slab, stream);
+#define LZB_LAUNCH(S, GG) launch_variant<S, GG>(g, ctas, d_packed, d_out, d_units, d_results, n_units, d_ticket, d_model_slab, stream)
+  if (!g.shared_model) e = LZB_LAUNCH(false, 32);
+  else if (g.group == 32) e = LZB_LAUNCH(true, 32);
+  else if (g.group == 16) e = LZB_LAUNCH(true, 16);
+  else if (g.group == 8) e = LZB_LAUNCH(true, 8);
+  else e = LZB_LAUNCH(true, 4);
+#undef LZB_LAUNCH
   return (int)e;
 }
 

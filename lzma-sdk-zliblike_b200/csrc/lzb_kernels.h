@@ -8,8 +8,8 @@
 
 #include "lzb_types.h"
 
-#define LZB_MAX_WARPS_PER_CTA 32
-#define LZB_DEFAULT_WARPS_PER_CTA 24
+#define LZB_DEFAULT_GROUP 16            /* lanes per unit: 16 = two units per warp (measured best, profiles/r01_c_residency.md) */
+#define LZB_DEFAULT_UNITS_PER_SM 36
 #define LZB_MAX_SHARED_MODEL_BYTES (56u * 1024u)
 
 #ifdef __cplusplus
@@ -18,12 +18,14 @@ extern "C" {
 
 typedef struct LzbGeometry
 {
-  uint32_t warps_per_cta;   /* resident units per SM                                   */
-  uint32_t ctas;            /* one per SM                                              */
-  uint32_t region_bytes;    /* shared-memory bytes per warp (model / post-pass scratch) */
-  uint32_t slab_stride;     /* HBM slab bytes per warp (matched-literal trees, or the whole model) */
+  uint32_t group;           /* lanes per unit (G)                                        */
+  uint32_t warps_per_cta;
+  uint32_t units_per_cta;   /* resident units per SM = warps_per_cta * 32 / group        */
+  uint32_t ctas;            /* one per SM                                                */
+  uint32_t region_bytes;    /* shared-memory bytes per unit (model / post-pass scratch)  */
+  uint32_t slab_stride;     /* HBM slab bytes per unit (matched-literal trees, or the whole model) */
   int shared_model;
-  size_t slab_bytes;        /* slab the caller must provide: ctas * warps_per_cta * slab_stride */
+  size_t slab_bytes;        /* slab the caller must provide: ctas * units_per_cta * slab_stride */
 } LzbGeometry;
 
 /* Residency the decode kernel will use for a model of the given shared / HBM part sizes (bytes). */

@@ -1,8 +1,9 @@
-/* lzb_post.cuh -- what runs on a unit's bytes right after its decode, by the same warp, in the same
- * launch ("fused after decode"): the x86 BCJ / Delta post-filter in place, then CRC-32 / CRC-64.
+/* lzb_post.cuh -- what runs on a unit's bytes right after its decode, by the same G-lane group, in the
+ * same launch ("fused after decode"): the x86 BCJ / Delta post-filter in place, then CRC-32 / CRC-64.
  *
- * The warp's probability region in shared memory is dead once the unit is decoded; it is reused as
- * scratch here (CRC tables, or the Delta filter's per-lane column sums) -- kPostScratchBytes of it.
+ * The group's model storage is dead once the unit is decoded and is reused as scratch here: the CRC
+ * table (kPostSmemBytes of the shared-memory region) and the Delta filter's per-lane column sums
+ * (kPostScratchBytes of the matched-literal slab slice in HBM/L2).
  *
  *  x86 BCJ  (Bra86.c:11-85)   sequential state (3-bit history of recent E8/E9 candidates) resets after
  *           four bytes without an opcode candidate, and a conversion never reaches across such a gap;
@@ -11,7 +12,7 @@
  *  Delta    (Delta.c:43-62)   out[i] = in[i] + out[i-d] is a prefix sum per residue class mod d:
  *           per-lane column sums -> exclusive scan across lanes -> second sweep.
  *  CRC      (7zCrc.c, 7zCrcOpt.c, XzCrc64.c)  per-lane register over a contiguous segment, then the
- *           32 partial registers are aligned with x^(8*bytes_after) mod P and XOR-reduced.
+ *           G partial registers are aligned with x^(8*bytes_after) mod P and XOR-reduced.
  */
 #pragma once
 
@@ -24,15 +25,7 @@ constexpr uint32_t kPostSmemBytes = 2048;                    /* CRC-64 table: 25
 constexpr uint32_t kPoly32 = 0xEDB88320u;                    /* 7zCrc.c:7  */
 constexpr uint64_t kPoly64 = 0xC96C5795D7870F42ull;          /* XzCrc64.c:6 */
 
-#ifdef LZB_EMU
-template <class T> static inline T lzb_shfl_xor(T v, int) { return v; }
-template <class T> static inline T lzb_shfl_down(T v, int) { return v; }
-#else
-template <class T> __device__ __forceinline__ T lzb_shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-template <class T> __device__ __forceinline__ T lzb_shfl_down(T v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
-#endif
-
-/* ------------------------------------------------------------------ x86 BCJ, decode direction --- */
+/* ------------------------------------------------------------------ x86 BCJ ---------------------- */
 LZB_FN bool is_opcode(uint8_t b) { return (b & 0xFE) == 0xE8; }
 LZB_FN bool is_fill(uint8_t b) { return b == 0x00 || b == 0xFF; }
 
@@ -88,14 +81,15 @@ LZB_FN uint32_t x86_convert_range(uint8_t *data, uint32_t from, uint32_t to, uin
 }
 
 /* Whole-buffer x86_Convert.  Returns the processed byte count; *state in/out as in the reference. */
-LZB_FN uint32_t x86_convert_warp(uint8_t *data, uint32_t size, uint32_t ip, bool encoding, uint32_t &state)
+template <uint32_t G> LZB_FN uint32_t x86_convert_group(uint8_t *data, uint32_t size, uint32_t ip, bool encoding, uint32_t &state)
 {
+  typedef Group<G> Grp;
   if (size < 5) return 0;                               /* Bra86.c:15-16 (state untouched) */
   const uint32_t stop = size - 4;                       /* candidates live in [0, stop) */
-  const uint32_t lane = lzb_lane();
-  const uint32_t seg = (stop + LZB_LANES - 1) / LZB_LANES;
+  const uint32_t lane = Grp::lane();
+  const uint32_t seg = (stop + G - 1) / G;
   uint32_t start;
-  lzb_syncwarp();
+  Grp::sync();
   if (lane == 0) start = 0;
   else
   {
@@ -111,63 +105,66 @@ LZB_FN uint32_t x86_convert_warp(uint8_t *data, uint32_t size, uint32_t ip, bool
     }
     if (start > stop) start = stop;
   }
-  uint32_t next = lzb_shfl_down(start, 1);
-  if (lane == LZB_LANES - 1) next = stop;
-  lzb_syncwarp();                                        /* all safe points found on unmodified bytes */
+  uint32_t next = Grp::shfl_down(start, 1);
+  if (lane == G - 1) next = stop;
+  Grp::sync();                                           /* all safe points found on unmodified bytes */
   uint32_t hist = lane == 0 ? (state & 7) : 0;
   uint32_t last = lane == 0 ? 0xFFFFFFFFu : start - 5;   /* lane 0: prevPosT = -1 (Bra86.c:18); others: far */
   uint32_t pos = start;
   const bool busy = start < next;
   if (busy) pos = x86_convert_range(data, start, next, ip, encoding, hist, last);
-  lzb_syncwarp();
+  Grp::sync();
   /* the scan's final (pos, last, hist) are those of the last lane that owned a range */
-#ifndef LZB_EMU
-  const uint32_t owners = __ballot_sync(0xffffffffu, busy);
-  const int top = 31 - __clz((int)owners);
-  pos = __shfl_sync(0xffffffffu, pos, top);
-  last = __shfl_sync(0xffffffffu, last, top);
-  hist = __shfl_sync(0xffffffffu, hist, top);
+  const uint32_t owners = Grp::ballot(busy);
+#ifdef LZB_EMU
+  const uint32_t top = 31u - (uint32_t)__builtin_clz(owners | 1u);
+#else
+  const uint32_t top = 31u - (uint32_t)__clz((int)(owners | 1u));
 #endif
+  pos = Grp::bcast(pos, top);
+  last = Grp::bcast(last, top);
+  hist = Grp::bcast(hist, top);
   const uint32_t gap = pos - last;
   state = gap > 3 ? 0 : ((hist << (gap - 1)) & 7);      /* Bra86.c:82-83 */
   return pos;
 }
 
 /* ------------------------------------------------------------------ Delta ---------------------- */
-LZB_FN void delta_decode_warp(uint8_t *data, uint32_t size, uint32_t dist, uint8_t *acc /* dist*LANES bytes */)
+template <uint32_t G> LZB_FN void delta_decode_group(uint8_t *data, uint32_t size, uint32_t dist, uint8_t *acc /* dist*G bytes */)
 {
-  const uint32_t lane = lzb_lane();
+  typedef Group<G> Grp;
+  const uint32_t lane = Grp::lane();
   const uint32_t rows = (size + dist - 1) / dist;
-  const uint32_t seg = ((rows + LZB_LANES - 1) / LZB_LANES) * dist;
+  const uint32_t seg = ((rows + G - 1) / G) * dist;
   const uint32_t begin = (uint64_t)lane * seg < size ? lane * seg : size;
   const uint32_t end = size - begin < seg ? size : begin + seg;
-  lzb_syncwarp();
-  for (uint32_t c = 0; c < dist; c++) acc[c * LZB_LANES + lane] = 0;
+  Grp::sync();
+  for (uint32_t c = 0; c < dist; c++) acc[c * G + lane] = 0;
   for (uint32_t i = begin, c = 0; i < end; i++)
   {
-    acc[c * LZB_LANES + lane] = (uint8_t)(acc[c * LZB_LANES + lane] + data[i]);
+    acc[c * G + lane] = (uint8_t)(acc[c * G + lane] + data[i]);
     if (++c == dist) c = 0;
   }
-  lzb_syncwarp();
-  for (uint32_t c = lane; c < dist; c += LZB_LANES)     /* exclusive scan across lanes, per column */
+  Grp::sync();
+  for (uint32_t c = lane; c < dist; c += G)              /* exclusive scan across lanes, per column */
   {
     uint8_t run = 0;
-    for (uint32_t l = 0; l < LZB_LANES; l++)
+    for (uint32_t l = 0; l < G; l++)
     {
-      const uint8_t t = acc[c * LZB_LANES + l];
-      acc[c * LZB_LANES + l] = run;
+      const uint8_t t = acc[c * G + l];
+      acc[c * G + l] = run;
       run = (uint8_t)(run + t);
     }
   }
-  lzb_syncwarp();
+  Grp::sync();
   for (uint32_t i = begin, c = 0; i < end; i++)
   {
-    const uint8_t v = (uint8_t)(acc[c * LZB_LANES + lane] + data[i]);
-    acc[c * LZB_LANES + lane] = v;
+    const uint8_t v = (uint8_t)(acc[c * G + lane] + data[i]);
+    acc[c * G + lane] = v;
     data[i] = v;
     if (++c == dist) c = 0;
   }
-  lzb_syncwarp();
+  Grp::sync();
 }
 
 /* ------------------------------------------------------------------ CRC ------------------------ */
@@ -206,64 +203,66 @@ LZB_FN uint64_t xpow64(uint32_t n)
   return r;
 }
 
-LZB_FN void lane_segment(uint32_t size, uint32_t &begin, uint32_t &end)
+template <uint32_t G> LZB_FN void lane_segment(uint32_t size, uint32_t &begin, uint32_t &end)
 {
-  const uint32_t lane = lzb_lane();
-  uint32_t seg = (size + LZB_LANES - 1) / LZB_LANES;
+  const uint32_t lane = Group<G>::lane();
+  uint32_t seg = (size + G - 1) / G;
   seg = (seg + 15u) & ~15u;
   begin = (uint64_t)lane * seg < size ? lane * seg : size;
   end = size - begin < seg ? size : begin + seg;
 }
 
 /* CRC-32 as CrcCalc (7zCrc.c:44): preset all-ones, final inversion */
-LZB_FN uint32_t crc32_warp(const uint8_t *data, uint32_t size, uint32_t *table /* 256 entries */)
+template <uint32_t G> LZB_FN uint32_t crc32_group(const uint8_t *data, uint32_t size, uint32_t *table /* 256 entries */)
 {
-  const uint32_t lane = lzb_lane();
-  lzb_syncwarp();
-  for (uint32_t i = lane; i < 256; i += LZB_LANES)          /* CrcGenerateTable, 7zCrc.c:49-60 */
+  typedef Group<G> Grp;
+  const uint32_t lane = Grp::lane();
+  Grp::sync();
+  for (uint32_t i = lane; i < 256; i += G)               /* CrcGenerateTable, 7zCrc.c:49-60 */
   {
     uint32_t r = i;
     for (int k = 0; k < 8; k++) r = (r >> 1) ^ (kPoly32 & (0u - (r & 1)));
     table[i] = r;
   }
-  lzb_syncwarp();
+  Grp::sync();
   uint32_t begin, end;
-  lane_segment(size, begin, end);
+  lane_segment<G>(size, begin, end);
   uint32_t v = lane == 0 ? 0xFFFFFFFFu : 0u;
   for (uint32_t i = begin; i < end; i++) v = table[(v ^ data[i]) & 0xFF] ^ (v >> 8);
   v = mulmod32(v, xpow32(size - end));
-  for (uint32_t m = LZB_LANES >> 1; m != 0; m >>= 1) v ^= lzb_shfl_xor(v, (int)m);
-  lzb_syncwarp();
+  for (uint32_t m = G >> 1; m != 0; m >>= 1) v ^= Grp::shfl_xor(v, m);
+  Grp::sync();
   return v ^ 0xFFFFFFFFu;
 }
 
 /* CRC-64/XZ as Crc64Calc (XzCrc64.c:30) */
-LZB_FN uint64_t crc64_warp(const uint8_t *data, uint32_t size, uint64_t *table /* 256 entries */)
+template <uint32_t G> LZB_FN uint64_t crc64_group(const uint8_t *data, uint32_t size, uint64_t *table /* 256 entries */)
 {
-  const uint32_t lane = lzb_lane();
-  lzb_syncwarp();
-  for (uint32_t i = lane; i < 256; i += LZB_LANES)          /* Crc64GenerateTable, XzCrc64.c:9-20 */
+  typedef Group<G> Grp;
+  const uint32_t lane = Grp::lane();
+  Grp::sync();
+  for (uint32_t i = lane; i < 256; i += G)               /* Crc64GenerateTable, XzCrc64.c:9-20 */
   {
     uint64_t r = i;
     for (int k = 0; k < 8; k++) r = (r >> 1) ^ (kPoly64 & (0ull - (r & 1)));
     table[i] = r;
   }
-  lzb_syncwarp();
+  Grp::sync();
   uint32_t begin, end;
-  lane_segment(size, begin, end);
+  lane_segment<G>(size, begin, end);
   uint64_t v = lane == 0 ? ~0ull : 0ull;
   for (uint32_t i = begin; i < end; i++) v = table[(v ^ data[i]) & 0xFF] ^ (v >> 8);
   v = mulmod64(v, xpow64(size - end));
-  for (uint32_t m = LZB_LANES >> 1; m != 0; m >>= 1) v ^= lzb_shfl_xor(v, (int)m);
-  lzb_syncwarp();
+  for (uint32_t m = G >> 1; m != 0; m >>= 1) v ^= Grp::shfl_xor(v, m);
+  Grp::sync();
   return ~v;
 }
 
-/* filter -> check -> verdict, for one decoded unit.  `scratch` = the warp's dead probability region. */
-/* `scratch`     : >= kPostSmemBytes of the warp's (dead) shared-memory model region -- CRC table.
- * `big_scratch` : >= kPostScratchBytes, the warp's (dead) matched-literal slab slice in HBM/L2 -- Delta
- *                 column sums (up to 256 x 32 bytes; Delta blocks are rare, L2 latency is acceptable). */
-LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t *scratch, uint8_t *big_scratch)
+/* filter -> check -> verdict, for one decoded unit.
+ * `scratch`     : >= kPostSmemBytes of the group's (dead) shared-memory model region -- CRC table.
+ * `big_scratch` : >= kPostScratchBytes, the group's (dead) matched-literal slab slice in HBM/L2 -- Delta
+ *                 column sums (up to 256 x G bytes; Delta blocks are rare, L2 latency is acceptable). */
+template <uint32_t G> LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t *scratch, uint8_t *big_scratch)
 {
   if (r.res != LZB_SZ_OK) return;
   const uint32_t n = r.dst_done;
@@ -271,12 +270,12 @@ LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t 
   {
     /* stand-alone x86_Convert calls pass the direction in flags bit 1 and the history in `expect` */
     uint32_t st = (uint32_t)(u.expect >> 32) & 7;
-    const uint32_t done = x86_convert_warp(data, n, u.filter_param, (u.flags & 2) != 0, st);
+    const uint32_t done = x86_convert_group<G>(data, n, u.filter_param, (u.flags & 2) != 0, st);
     if (u.flags & 4) { r.src_used = done; r.status = (int32_t)st; }   /* stand-alone call: report them */
   }
-  else if (u.filter == LZB_FILTER_DELTA) delta_decode_warp(data, n, u.filter_param, big_scratch);
-  if (u.check == LZB_CHECK_CRC32) r.check = crc32_warp(data, n, reinterpret_cast<uint32_t *>(scratch));
-  else if (u.check == LZB_CHECK_CRC64) r.check = crc64_warp(data, n, reinterpret_cast<uint64_t *>(scratch));
+  else if (u.filter == LZB_FILTER_DELTA) delta_decode_group<G>(data, n, u.filter_param, big_scratch);
+  if (u.check == LZB_CHECK_CRC32) r.check = crc32_group<G>(data, n, reinterpret_cast<uint32_t *>(scratch));
+  else if (u.check == LZB_CHECK_CRC64) r.check = crc64_group<G>(data, n, reinterpret_cast<uint64_t *>(scratch));
   if ((u.flags & LZB_UNIT_VERIFY) && u.check != LZB_CHECK_NONE && r.check != u.expect) r.res = LZB_SZ_ERROR_CRC;
 }
 

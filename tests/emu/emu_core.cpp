@@ -1,10 +1,10 @@
 /* emu_core.cpp -- TEST-ONLY host build of the device decode logic.
  *
- * Compiles lzma-sdk-zliblike_b200/csrc/lzb_core.cuh + lzb_post.cuh with -DLZB_EMU (one emulated lane)
- * so that `pytest -m "not gpu"` can exercise the kernel's symbol grammar, finish-mode/lookahead
- * driver and LZMA2 chunk machine against the oracle on machines without a GPU.  It is NOT a CPU
- * fallback: nothing in the product package loads this library, and the product fails loudly when
- * the CUDA library or a device is missing.
+ * Compiles lzma-sdk-zliblike_b200/csrc/lzb_core.cuh + lzb_post.cuh with -DLZB_EMU (one emulated lane per
+ * unit, G = 1) so that `pytest -m "not gpu"` can exercise the kernel's symbol grammar, the driver state
+ * machine (finish modes, look-ahead, LZMA2 chunk layer, resume) and the post-filters against the oracle on
+ * machines without a GPU.  It is NOT a CPU fallback: nothing in the product package loads this library,
+ * and the product fails loudly when the CUDA library or a device is missing.
  */
 #define LZB_EMU 1
 #include <stdlib.h>
@@ -22,12 +22,13 @@ extern "C" int emu_post_units(uint8_t *data, const LzbUnit *units, LzbResult *re
     const LzbUnit &u = units[i];
     LzbResult r;
     r.res = LZB_SZ_OK; r.status = LZB_ST_NOT_SPECIFIED; r.src_used = 0; r.dst_done = u.dst_cap; r.check = 0;
-    lzb::post_process(u, r, data + u.dst_off, scratch.data(), scratch.data());
+    lzb::post_process<1>(u, r, data + u.dst_off, scratch.data(), scratch.data());
     results[i] = r;
   }
   return 0;
 }
 
+/* the kernel's loop, for one group: fetch -> advance -> (step)* -> ... -> finish */
 extern "C" int emu_decode_units(const uint8_t *packed, uint8_t *out, const LzbUnit *units, LzbResult *results,
                                 uint32_t n)
 {
@@ -43,12 +44,19 @@ extern "C" int emu_decode_units(const uint8_t *packed, uint8_t *out, const LzbUn
     if (ng * 2 < lzb::kPostScratchBytes) ng = lzb::kPostScratchBytes / 2;
     probs.assign(ns, 0xDEAD);       /* poison: every model entry must be initialised by the decoder */
     matched.assign(ng, 0xDEAD);
-    lzb::UnitDecoder d;
+    lzb::UnitDecoderT<1> d;
     const bool stateful = (u.flags & LZB_UNIT_STATEFUL) != 0;
     d.begin(packed + u.src_off, u.src_len, out + u.dst_off, stateful ? u.filter_param : u.dst_cap, u.dict_size,
             probs.data(), matched.data());
-    lzb::decode_unit(d, u, r, stateful ? reinterpret_cast<LzbStreamState *>((uintptr_t)u.expect) : nullptr);
-    if (!stateful) lzb::post_process(u, r, out + u.dst_off, (uint8_t *)probs.data(), (uint8_t *)matched.data());
+    d.start_unit(u, stateful ? reinterpret_cast<LzbStreamState *>((uintptr_t)u.expect) : nullptr);
+    for (;;)
+    {
+      if (d.st != lzb::S_RUN) d.advance();
+      if (d.st == lzb::S_UNIT_END) break;
+      d.step();
+    }
+    d.finish_unit(r);
+    if (!stateful) lzb::post_process<1>(u, r, out + u.dst_off, (uint8_t *)probs.data(), (uint8_t *)matched.data());
     results[i] = r;
   }
   return 0;

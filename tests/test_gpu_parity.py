@@ -42,13 +42,28 @@ class Gpu:
         return lzb200.sdk.crc64(data)
 
 
-@pytest.fixture(scope="module")
-def gpu():
-    return Gpu()
+# Lanes per unit (lzb_kernels.cu): "auto" is what a user gets (two units per warp, or one when the launch
+# has few units); 16 and 8 force the several-units-per-warp loops on the small test launches too.
+GROUPS = ["auto", "16", "8"]
+
+
+def _set_group(g):
+    import os
+    if g == "auto":
+        os.environ.pop("LZB_GROUP", None)
+    else:
+        os.environ["LZB_GROUP"] = g
+
+
+@pytest.fixture(scope="module", params=GROUPS)
+def gpu(request):
+    _set_group(request.param)
+    yield Gpu()
+    _set_group("auto")
 
 
 @pytest.fixture(scope="module")
-def ctx():
+def ctx(gpu):
     c = lzb200.lib.Context(0)
     yield c
     c.close()
@@ -126,7 +141,7 @@ def test_batch_matches_per_stream_calls(gpu, ora, ctx):
         assert np.array_equal(d["out"][: d["dest_len"]], want["out"][: want["dest_len"]]), i
 
 
-def test_many_units_digest_of_digests(ctx, ora):
+def test_many_units_digest_of_digests(gpu, ctx, ora):
     """4096 raw LZMA units through Lzb_DecodeUnitsHost with the CRC-32 fused on the GPU: every unit must verify
     against the digest of its plain text, and the XOR of all GPU digests equals the host's."""
     blobs, _ = cases.golden()

@@ -389,9 +389,10 @@ def main():
         except Exception:
             traffic = None
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                    kernel="lzb_decode_units_kernel<shared model>", launches_per_step=1, kernel_ms=kms,
+                    kernel="lzb_decode_units_kernel<shared model, G lanes per unit>", launches_per_step=1, kernel_ms=kms,
                     algorithmic_bytes_per_launch=int(t["sum_p"] + t["sum_u"]), peak_source=peak_src,
-                    note="serial range-decoder chain: issue/latency-bound by design, far below the HBM roof (DESIGN.md)")
+                    note="serial range-decoder chain: bound by resident units x issue slots, far below the HBM roof; "
+                         "traffic above the algorithmic bytes = match sources evicted from L2 (profiles/r01_c_residency.md)")
 
     # ---------------- CPU baseline on this box (rank 0, N=1 only), bounded sample
     cpu = None

@@ -165,29 +165,127 @@ UInt64 Crc64Calc(const void *data, size_t size);
 SizeT x86_Convert(Byte *data, SizeT size, UInt32 ip, UInt32 *state, int encoding);
 #define DELTA_STATE_SIZE 256
 void Delta_Init(Byte *state);
+void Delta_Encode(Byte *state, unsigned delta, Byte *data, SizeT size);
 void Delta_Decode(Byte *state, unsigned delta, Byte *data, SizeT size);
 
-/* ---- xz: reference Xz.h:21,54,85-96,136-148,223-248 ---- */
+/* ---- xz: reference Xz.h (ids :11-19, block :33-54, check :66-85, coders :136-185, unpacker :187-248),
+ *      Sha256.h:13-22.  The structs below are ABI (callers allocate them and read their fields), so they
+ *      keep the reference's field order and sizes: CXzBlock 152, CXzCheck 120, IStateCoder 40,
+ *      CMixCoder 272, CXzUnpacker 1792 bytes on x86-64 (asserted in tests/test_abi_and_host.py). ---- */
+#define XZ_ID_Delta 3
+#define XZ_ID_X86 4
+#define XZ_ID_PPC 5
+#define XZ_ID_IA64 6
+#define XZ_ID_ARM 7
+#define XZ_ID_ARMT 8
+#define XZ_ID_SPARC 9
+#define XZ_ID_LZMA2 0x21
+#define XZ_CHECK_NO 0
+#define XZ_CHECK_CRC32 1
+#define XZ_CHECK_CRC64 4
+#define XZ_CHECK_SHA256 10
+#define XZ_BLOCK_HEADER_SIZE_MAX 1024
+#define XZ_NUM_FILTERS_MAX 4
+#define XZ_FILTER_PROPS_SIZE_MAX 20
+#define SHA256_DIGEST_SIZE 32
+
+typedef struct { UInt32 state[8]; UInt64 count; Byte buffer[64]; } CSha256;
+void Sha256_Init(CSha256 *p);
+void Sha256_Update(CSha256 *p, const Byte *data, size_t size);
+void Sha256_Final(CSha256 *p, Byte *digest);
+
 typedef enum { CODER_STATUS_NOT_SPECIFIED, CODER_STATUS_FINISHED_WITH_MARK, CODER_STATUS_NOT_FINISHED,
                CODER_STATUS_NEEDS_MORE_INPUT } ECoderStatus;
 typedef enum { CODER_FINISH_ANY, CODER_FINISH_END } ECoderFinishMode;
 typedef UInt16 CXzStreamFlags;
 unsigned Xz_ReadVarInt(const Byte *p, size_t maxSize, UInt64 *value);
+unsigned Xz_WriteVarInt(Byte *buf, UInt64 v);
 unsigned XzFlags_GetCheckSize(CXzStreamFlags f);
 SRes Xz_ParseHeader(CXzStreamFlags *p, const Byte *buf);
 
-/* Xz.h:194-221: same size as the reference object (1792 bytes) so callers' storage fits; the content
- * is this library's own (host-side container state; block payloads are decoded on the GPU). */
-typedef struct { UInt64 opaque[224]; } CXzUnpacker;
+typedef struct { UInt64 id; UInt32 propsSize; Byte props[XZ_FILTER_PROPS_SIZE_MAX]; } CXzFilter;
+typedef struct { UInt64 packSize; UInt64 unpackSize; Byte flags; CXzFilter filters[XZ_NUM_FILTERS_MAX]; } CXzBlock;
+#define XzBlock_GetNumFilters(p) (((p)->flags & 3) + 1)
+#define XzBlock_HasPackSize(p)   (((p)->flags & (1 << 6)) != 0)
+#define XzBlock_HasUnpackSize(p) (((p)->flags & (1 << 7)) != 0)
+SRes XzBlock_Parse(CXzBlock *p, const Byte *header);                  /* XzDec.c:505-556 */
+
+typedef struct { int mode; UInt32 crc; UInt64 crc64; CSha256 sha; } CXzCheck;
+void XzCheck_Init(CXzCheck *p, int mode);                             /* Xz.c:45-88; digests computed on the GPU */
+void XzCheck_Update(CXzCheck *p, const void *data, size_t size);
+int XzCheck_Final(CXzCheck *p, Byte *digest);
+
+typedef struct _IStateCoder
+{
+  void *p;
+  void (*Free)(void *p, ISzAlloc *alloc);
+  SRes (*SetProps)(void *p, const Byte *props, size_t propSize, ISzAlloc *alloc);
+  void (*Init)(void *p);
+  SRes (*Code)(void *p, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
+               int srcWasFinished, ECoderFinishMode finishMode, int *wasFinished);
+} IStateCoder;
+
+#define MIXCODER_NUM_FILTERS_MAX 4
+typedef struct
+{
+  ISzAlloc *alloc;
+  Byte *buf;
+  int numCoders;
+  int finished[MIXCODER_NUM_FILTERS_MAX - 1];
+  size_t pos[MIXCODER_NUM_FILTERS_MAX - 1];
+  size_t size[MIXCODER_NUM_FILTERS_MAX - 1];
+  UInt64 ids[MIXCODER_NUM_FILTERS_MAX];
+  IStateCoder coders[MIXCODER_NUM_FILTERS_MAX];
+} CMixCoder;
+
+/* The resumable filter chain of an xz block (XzDec.c:356-480): LZMA2 first (stateful, on the GPU), then
+ * x86 BCJ / Delta over a 16 KiB staging buffer exactly as BraState_Code does.  The other branch converters
+ * (PPC, IA64, ARM, ARMT, SPARC) are not on the hot path: SetFromMethod returns SZ_ERROR_UNSUPPORTED. */
+void MixCoder_Construct(CMixCoder *p, ISzAlloc *alloc);
+void MixCoder_Free(CMixCoder *p);
+void MixCoder_Init(CMixCoder *p);
+SRes MixCoder_SetFromMethod(CMixCoder *p, int coderIndex, UInt64 methodId);
+SRes MixCoder_Code(CMixCoder *p, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen, int srcWasFinished,
+                   ECoderFinishMode finishMode, ECoderStatus *status);
+SRes XzDec_Init(CMixCoder *p, const CXzBlock *block);                 /* XzDec.c:558-588 */
+
+typedef enum { XZ_STATE_STREAM_HEADER, XZ_STATE_STREAM_INDEX, XZ_STATE_STREAM_INDEX_CRC, XZ_STATE_STREAM_FOOTER,
+               XZ_STATE_STREAM_PADDING, XZ_STATE_BLOCK_HEADER, XZ_STATE_BLOCK, XZ_STATE_BLOCK_FOOTER } EXzState;
+
+typedef struct
+{
+  EXzState state;
+  UInt32 pos;
+  unsigned alignPos;
+  unsigned indexPreSize;
+  CXzStreamFlags streamFlags;
+  UInt32 blockHeaderSize;
+  UInt64 packSize;
+  UInt64 unpackSize;
+  UInt64 numBlocks;
+  UInt64 indexSize;
+  UInt64 indexPos;
+  UInt64 padSize;
+  UInt64 numStreams;
+  UInt32 crc;
+  CMixCoder decoder;
+  CXzBlock block;
+  CXzCheck check;
+  CSha256 sha;
+  Byte shaDigest[SHA256_DIGEST_SIZE];
+  Byte buf[XZ_BLOCK_HEADER_SIZE_MAX];
+} CXzUnpacker;
+
 SRes XzUnpacker_Create(CXzUnpacker *p, ISzAlloc *alloc);
 void XzUnpacker_Free(CXzUnpacker *p);
-/* Contract of Xz.h:223-246.  Round-1 limit: each call must present whole blocks (any number of them,
- * with the headers/index/footer around them) and room for their output; a call that would have to
- * suspend inside a block returns SZ_ERROR_UNSUPPORTED instead of falling back to a CPU decoder. */
+/* Contract of Xz.h:223-246 / XzDec.c:604-870, resumable at any byte: the container state machine runs on
+ * the host; block payloads are decoded on the GPU.  Whole blocks found in `src` with room for their output
+ * in `dest` are decoded in parallel in one pass (all of them, and the dictionary-reset groups inside them);
+ * a block that is cut by the end of `src` or `dest` goes through the resumable chain (MixCoder_Code). */
 SRes XzUnpacker_Code(CXzUnpacker *p, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
                      int finishMode, ECoderStatus *status);
 Bool XzUnpacker_IsStreamWasFinished(CXzUnpacker *p);
-UInt64 XzUnpacker_GetNumBlocks(const CXzUnpacker *p);   /* reads what callers take from p->numBlocks */
+UInt64 XzUnpacker_GetNumBlocks(const CXzUnpacker *p);   /* p->numBlocks of the current stream */
 
 /* ====================================================================================== */
 /* Part 2 -- batched extension (no reference analogue)                                     */

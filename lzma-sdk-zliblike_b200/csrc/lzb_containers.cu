@@ -12,6 +12,8 @@
  * return what the reference's sequential decoder returns: the first failing unit decides.
  */
 #include "lzb_host.h"
+#include "lzb_xz.h"
+#include "lzb_sha256.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -190,16 +192,17 @@ extern "C" SRes Lzma2Decode(Byte *dest, SizeT *destLen, const Byte *src, SizeT *
 static const Byte k_xz_magic[6] = { 0xFD, '7', 'z', 'X', 'Z', 0 };
 
 /* host CRC-32 of a few header bytes (container framing only; payload digests run on the GPU) */
-static uint32_t small_crc32(const Byte *p, size_t n)
+uint32_t lzb_small_crc32_update(uint32_t reg, const Byte *p, size_t n)
 {
-  uint32_t v = 0xFFFFFFFFu;
   for (size_t i = 0; i < n; i++)
   {
-    v ^= p[i];
-    for (int k = 0; k < 8; k++) v = (v >> 1) ^ (0xEDB88320u & (0u - (v & 1)));
+    reg ^= p[i];
+    for (int k = 0; k < 8; k++) reg = (reg >> 1) ^ (0xEDB88320u & (0u - (reg & 1)));
   }
-  return ~v;
+  return reg;
 }
+
+uint32_t lzb_small_crc32(const Byte *p, size_t n) { return ~lzb_small_crc32_update(0xFFFFFFFFu, p, n); }
 
 extern "C" unsigned Xz_ReadVarInt(const Byte *p, size_t maxSize, UInt64 *value)
 {
@@ -215,7 +218,7 @@ extern "C" unsigned Xz_ReadVarInt(const Byte *p, size_t maxSize, UInt64 *value)
   return 0;
 }
 
-static unsigned write_varint(Byte *buf, UInt64 v)
+extern "C" unsigned Xz_WriteVarInt(Byte *buf, UInt64 v)
 {
   unsigned i = 0;
   do { buf[i++] = (Byte)((v & 0x7F) | 0x80); v >>= 7; } while (v != 0);
@@ -233,47 +236,45 @@ extern "C" SRes Xz_ParseHeader(CXzStreamFlags *p, const Byte *buf)
 {
   /* reference XzDec.c:482-489 */
   *p = (CXzStreamFlags)(((unsigned)buf[6] << 8) | buf[7]);
-  if (small_crc32(buf + 6, 2) != lzb_le32(buf + 8)) return SZ_ERROR_NO_ARCHIVE;
+  if (lzb_small_crc32(buf + 6, 2) != lzb_le32(buf + 8)) return SZ_ERROR_NO_ARCHIVE;
   return *p <= 0xF ? SZ_OK : SZ_ERROR_UNSUPPORTED;
 }
 
-struct XzFilterSpec { UInt64 id; UInt32 props_size; Byte props[20]; };
-
 /* reference XzDec.c:505-556 */
-static SRes parse_block_header(const Byte *h, XzFilterSpec *f, int *nf)
+extern "C" SRes XzBlock_Parse(CXzBlock *p, const Byte *h)
 {
   const UInt32 hs = (UInt32)h[0] << 2;
   unsigned pos = 1;
-  UInt64 v;
-  if (small_crc32(h, hs) != lzb_le32(h + hs)) return SZ_ERROR_ARCHIVE;
+  if (lzb_small_crc32(h, hs) != lzb_le32(h + hs)) return SZ_ERROR_ARCHIVE;
   if (pos == hs) return SZ_ERROR_ARCHIVE;
-  const unsigned flags = h[pos++];
-  if (flags & 0x40)
+  p->flags = h[pos++];
+  if (XzBlock_HasPackSize(p))
   {
-    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &v);
+    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &p->packSize);
     if (!s) return SZ_ERROR_ARCHIVE;
     pos += s;
-    if (v == 0 || v + hs >= (UInt64)1 << 63) return SZ_ERROR_ARCHIVE;
+    if (p->packSize == 0 || p->packSize + hs >= (UInt64)1 << 63) return SZ_ERROR_ARCHIVE;
   }
-  if (flags & 0x80)
+  if (XzBlock_HasUnpackSize(p))
   {
-    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &v);
+    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &p->unpackSize);
     if (!s) return SZ_ERROR_ARCHIVE;
     pos += s;
   }
-  *nf = (int)(flags & 3) + 1;
-  for (int i = 0; i < *nf; i++)
+  const int nf = XzBlock_GetNumFilters(p);
+  for (int i = 0; i < nf; i++)
   {
+    CXzFilter &f = p->filters[i];
     UInt64 sz;
-    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &f[i].id);
+    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &f.id);
     if (!s) return SZ_ERROR_ARCHIVE;
     pos += s;
     s = Xz_ReadVarInt(h + pos, hs - pos, &sz);
     if (!s) return SZ_ERROR_ARCHIVE;
     pos += s;
-    if (sz > hs - pos || sz > 20) return SZ_ERROR_ARCHIVE;
-    f[i].props_size = (UInt32)sz;
-    memcpy(f[i].props, h + pos, (size_t)sz);
+    if (sz > hs - pos || sz > XZ_FILTER_PROPS_SIZE_MAX) return SZ_ERROR_ARCHIVE;
+    f.propsSize = (UInt32)sz;
+    memcpy(f.props, h + pos, (size_t)sz);
     pos += (unsigned)sz;
   }
   while (pos < hs) if (h[pos++] != 0) return SZ_ERROR_ARCHIVE;
@@ -282,24 +283,26 @@ static SRes parse_block_header(const Byte *h, XzFilterSpec *f, int *nf)
 
 /* Filter chains on the hot path: [x86 | delta] + LZMA2 (reference XzDec.c:63-106,356-371,558-588).
  * The other branch converters / longer chains are legal in the reference and out of scope here. */
-static SRes classify_chain(const XzFilterSpec *f, int nf, LzbXzBlock *b)
+SRes lzb_xz_classify_chain(const CXzBlock *blk, LzbXzBlock *b)
 {
-  const XzFilterSpec &last = f[nf - 1];
+  const int nf = XzBlock_GetNumFilters(blk);
+  const CXzFilter *f = blk->filters;
+  const CXzFilter &last = f[nf - 1];
   b->filter = LZB_FILTER_NONE; b->filter_param = 0;
-  if (last.id != 0x21 || last.props_size != 1 || last.props[0] > 40) return SZ_ERROR_UNSUPPORTED;
+  if (last.id != XZ_ID_LZMA2 || last.propsSize != 1 || last.props[0] > 40) return SZ_ERROR_UNSUPPORTED;
   b->lzma2_prop = last.props[0];
   if (nf == 1) return SZ_OK;
   if (nf > 2) { lzb_set_error("xz filter chains longer than 2 are outside the GPU hot path"); return SZ_ERROR_UNSUPPORTED; }
-  if (f[0].id == 3)
+  if (f[0].id == XZ_ID_Delta)
   {
-    if (f[0].props_size != 1) return SZ_ERROR_UNSUPPORTED;
+    if (f[0].propsSize != 1) return SZ_ERROR_UNSUPPORTED;
     b->filter = LZB_FILTER_DELTA; b->filter_param = (UInt32)f[0].props[0] + 1;
     return SZ_OK;
   }
-  if (f[0].id == 4)
+  if (f[0].id == XZ_ID_X86)
   {
-    if (f[0].props_size == 4) b->filter_param = lzb_le32(f[0].props);
-    else if (f[0].props_size != 0) return SZ_ERROR_UNSUPPORTED;
+    if (f[0].propsSize == 4) b->filter_param = lzb_le32(f[0].props);
+    else if (f[0].propsSize != 0) return SZ_ERROR_UNSUPPORTED;
     b->filter = LZB_FILTER_X86;
     return SZ_OK;
   }
@@ -308,37 +311,33 @@ static SRes classify_chain(const XzFilterSpec *f, int nf, LzbXzBlock *b)
 }
 
 /* ------------------------------------------------------------------ xz forward walk ----------- */
-struct XzWalk
-{
-  std::vector<LzbXzBlock> blocks;
-  std::vector<LzbUnit> units;          /* src_off absolute in the file, dst_off absolute in the output */
-  std::vector<SRes> after_block;       /* structural error met right after block k's payload (padding) */
-  SRes end_res = SZ_OK;                /* verdict if every walked block decodes and verifies */
-  int end_status = CODER_STATUS_NEEDS_MORE_INPUT;
-  size_t end_src = 0;
-  bool finished = false;
-  uint64_t out_total = 0;
-  int partial = -1;                    /* index of a block whose payload is cut short / malformed */
-};
-
-static void xz_walk(const Byte *src, size_t n, XzWalk &w)
+/* Forward walk.  in_blocks: `src` starts at a block header (or the index) of a stream whose header has been
+ * seen already (its flags are passed in); the index / footer verdicts are then meaningless to the caller,
+ * which takes only the block table. */
+void lzb_xz_walk(const Byte *src, size_t n, XzWalk &w, bool in_blocks, unsigned in_flags)
 {
   size_t ip = 0;
   uint64_t op = 0;
+  bool skip_header = in_blocks;
 #define XZ_END(code, st, at) do { w.end_res = (code); w.end_status = (st); w.end_src = (at); return; } while (0)
 #define XZ_STARVED() XZ_END(SZ_OK, CODER_STATUS_NEEDS_MORE_INPUT, n)
   for (;;)
   {
-    for (size_t k = 0; k < 6; k++)
+    CXzStreamFlags flags = (CXzStreamFlags)in_flags;
+    SRes r = SZ_OK;
+    if (!skip_header)
     {
-      if (ip + k >= n) XZ_STARVED();
-      if (src[ip + k] != k_xz_magic[k]) XZ_END(SZ_ERROR_NO_ARCHIVE, CODER_STATUS_NOT_SPECIFIED, ip + k);
+      for (size_t k = 0; k < 6; k++)
+      {
+        if (ip + k >= n) XZ_STARVED();
+        if (src[ip + k] != k_xz_magic[k]) XZ_END(SZ_ERROR_NO_ARCHIVE, CODER_STATUS_NOT_SPECIFIED, ip + k);
+      }
+      if (n - ip <= 12) XZ_STARVED();                /* the header is parsed when the next byte arrives */
+      r = Xz_ParseHeader(&flags, src + ip);
+      ip += 12;
+      if (r != SZ_OK) XZ_END(r, CODER_STATUS_NOT_SPECIFIED, ip);
     }
-    if (n - ip <= 12) XZ_STARVED();                  /* the header is parsed when the next byte arrives */
-    CXzStreamFlags flags;
-    SRes r = Xz_ParseHeader(&flags, src + ip);
-    ip += 12;
-    if (r != SZ_OK) XZ_END(r, CODER_STATUS_NOT_SPECIFIED, ip);
+    skip_header = false;
     const unsigned ctype = flags & 0xF, csz = XzFlags_GetCheckSize(flags);
     const size_t first_block = w.blocks.size();
 
@@ -348,17 +347,16 @@ static void xz_walk(const Byte *src, size_t n, XzWalk &w)
       if (src[ip] == 0) break;
       const UInt32 hs = ((UInt32)src[ip] << 2) + 4;
       if (n - ip <= hs) XZ_STARVED();
-      XzFilterSpec fs[4];
-      int nf = 0;
+      CXzBlock blk;
       LzbXzBlock b;
       memset(&b, 0, sizeof b);
-      r = parse_block_header(src + ip, fs, &nf);
+      memset(&blk, 0, sizeof blk);
+      r = XzBlock_Parse(&blk, src + ip);
       b.hdr_off = ip; b.hdr_size = hs;
       ip += hs;
       if (r != SZ_OK) XZ_END(r, CODER_STATUS_NOT_SPECIFIED, ip);
-      r = classify_chain(fs, nf, &b);
+      r = lzb_xz_classify_chain(&blk, &b);
       if (r != SZ_OK) XZ_END(r, CODER_STATUS_NOT_SPECIFIED, ip);
-      if (ctype == 10) { lzb_set_error("xz SHA-256 block check is outside the GPU hot path"); XZ_END(SZ_ERROR_UNSUPPORTED, CODER_STATUS_NOT_SPECIFIED, ip); }
       b.check_type = (uint8_t)ctype;
       UInt32 dict;
       lzma2_dict_size(b.lzma2_prop, &dict);
@@ -422,7 +420,7 @@ static void xz_walk(const Byte *src, size_t n, XzWalk &w)
     {
       const uint64_t nblk = w.blocks.size() - first_block;
       Byte pre[16];
-      const size_t pre_len = 1 + write_varint(pre + 1, nblk), idx_start = ip;
+      const size_t pre_len = 1 + Xz_WriteVarInt(pre + 1, nblk), idx_start = ip;
       pre[0] = 0;
       for (size_t k = 0; k < pre_len; k++)
       {
@@ -433,8 +431,8 @@ static void xz_walk(const Byte *src, size_t n, XzWalk &w)
       for (size_t k = first_block; k < w.blocks.size(); k++)
       {
         Byte t[24];
-        unsigned m = write_varint(t, w.blocks[k].pack_size + w.blocks[k].hdr_size + csz);
-        m += write_varint(t + m, w.blocks[k].unpack_size);
+        unsigned m = Xz_WriteVarInt(t, w.blocks[k].pack_size + w.blocks[k].hdr_size + csz);
+        m += Xz_WriteVarInt(t + m, w.blocks[k].unpack_size);
         rec.insert(rec.end(), t, t + m);
       }
       if (n - ip < rec.size()) XZ_STARVED();
@@ -449,13 +447,13 @@ static void xz_walk(const Byte *src, size_t n, XzWalk &w)
       if (!rec.empty() && memcmp(src + rec_at, rec.data(), rec.size()) != 0) XZ_END(SZ_ERROR_CRC, CODER_STATUS_NOT_SPECIFIED, ip);
       const size_t idx_len = ip - idx_start;
       if (n - ip < 4) XZ_STARVED();
-      const uint32_t crc = small_crc32(src + idx_start, idx_len);
+      const uint32_t crc = lzb_small_crc32(src + idx_start, idx_len);
       ip += 4;
       if (ip >= n) XZ_STARVED();
       if (crc != lzb_le32(src + ip - 4)) XZ_END(SZ_ERROR_CRC, CODER_STATUS_NOT_SPECIFIED, ip);
       if (n - ip < 12) XZ_STARVED();
       const Byte *f = src + ip;
-      const bool ok = (idx_len + 4 == (((size_t)lzb_le32(f + 4) + 1) << 2)) && lzb_le32(f) == small_crc32(f + 4, 6) &&
+      const bool ok = (idx_len + 4 == (((size_t)lzb_le32(f + 4) + 1) << 2)) && lzb_le32(f) == lzb_small_crc32(f + 4, 6) &&
                       flags == (((unsigned)f[8] << 8) | f[9]) && f[10] == 'Y' && f[11] == 'Z';
       ip += 12;
       if (!ok) XZ_END(SZ_ERROR_CRC, CODER_STATUS_NOT_SPECIFIED, ip);
@@ -471,60 +469,70 @@ static void xz_walk(const Byte *src, size_t n, XzWalk &w)
 #undef XZ_STARVED
 }
 
-extern "C" SRes XzDecodeParallel(LzbContext *c, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
-                                 ECoderStatus *status, UInt64 *numBlocks, int *streamFinished)
+/* ------------------------------------------------------------------ xz block prefetch --------- */
+/* Decode, in ONE batched GPU pass, the whole blocks at the front of src[0..n) -- all of them in parallel,
+ * and the dictionary-reset groups inside them -- into dest at the offsets a sequential decoder would give
+ * them, with BCJ/Delta applied and the check digest computed (not compared: XzUnpacker_Code does that when
+ * it reaches the block footer).  Only blocks whose units all decoded cleanly are reported; a block that is
+ * cut short, does not fit in dest, or fails is left to the resumable chain, which reproduces the reference's
+ * return values for it.  Advisory: returns the blocks it could do in `ready` (possibly none). */
+SRes lzb_xz_prefetch(LzbContext *c, const Byte *src, size_t n, bool in_blocks, unsigned flags, Byte *dest, size_t cap,
+                     std::vector<XzReady> &ready)
 {
-  const size_t cap = *destLen, in_size = *srcLen;
-  *destLen = *srcLen = 0;
-  *status = CODER_STATUS_NOT_SPECIFIED; *numBlocks = 0; *streamFinished = 0;
+  ready.clear();
+  XzWalk w;
+  lzb_xz_walk(src, n, w, in_blocks, flags);
+  /* prefix of blocks whose payload is all here and whose output fits */
+  size_t nb = 0, nu = 0;
+  for (; nb < w.blocks.size(); nb++)
+  {
+    const LzbXzBlock &b = w.blocks[nb];
+    if (b.complete == 0) break;
+    const uint64_t off = w.units[b.first_unit].dst_off;
+    if (off + b.unpack_size > cap) break;
+    nu = b.first_unit + b.n_units;
+  }
+  if (nb == 0) return SZ_OK;
+  w.blocks.resize(nb);
+  w.units.resize(nu);
   if (!c) c = lzb_default_context();
   if (!c) return SZ_ERROR_FAIL;
-  XzWalk w;
-  xz_walk(src, in_size, w);
-  if (w.units.empty())
-  {
-    *srcLen = w.end_src; *status = (ECoderStatus)w.end_status; *streamFinished = w.finished;
-    return w.end_res;
-  }
-  /* room: every walked block must fit (round-1 limit, include/lzb200.h) */
-  uint64_t need = 0;
-  for (auto &u : w.units) need = std::max<uint64_t>(need, u.dst_off + (u.dst_cap == 0xFFFFFFFFu ? 0 : u.dst_cap));
-  if (need > cap) { lzb_set_error("XzDecodeParallel: output buffer smaller than the walked blocks (%llu > %zu)", (unsigned long long)need, cap); return SZ_ERROR_UNSUPPORTED; }
-  for (auto &u : w.units) if ((uint64_t)u.dst_off + u.dst_cap > cap) u.dst_cap = (uint32_t)(cap - u.dst_off);
 
-  /* single-unit blocks: filter + digest fused into the decode launch; others: second pass */
-  std::vector<LzbUnit> post;
-  std::vector<size_t> post_block;
-  for (size_t k = 0; k < w.blocks.size(); k++)
+  /* single-unit blocks: filter + CRC fused into the decode launch; others (and SHA-256): second pass */
+  struct Post { size_t block; LzbUnit u; };
+  std::vector<Post> post;
+  for (size_t k = 0; k < nb; k++)
   {
     LzbXzBlock &b = w.blocks[k];
-    if (b.complete != 1) continue;
-    const bool has_check = b.check_type == LZB_CHECK_CRC32 || b.check_type == LZB_CHECK_CRC64;
-    if (b.filter == LZB_FILTER_NONE && !has_check) continue;
+    const bool crc = b.check_type == LZB_CHECK_CRC32 || b.check_type == LZB_CHECK_CRC64;
+    const bool sha = b.check_type == LZB_CHECK_SHA256;
+    if (b.filter == LZB_FILTER_NONE && !crc && !sha) continue;
+    bool second = sha;
     if (b.n_units == 1)
     {
       LzbUnit &u = w.units[b.first_unit];
       u.filter = (uint8_t)b.filter; u.filter_param = b.filter_param;
-      if (has_check) { u.check = b.check_type; u.flags |= LZB_UNIT_VERIFY; u.expect = b.expect; }
+      if (crc) u.check = b.check_type;
     }
-    else
+    else second = true;
+    if (second)
     {
-      LzbUnit u;
-      memset(&u, 0, sizeof u);
-      u.dst_off = w.units[b.first_unit].dst_off; u.dst_cap = (uint32_t)b.unpack_size;
-      u.filter = (uint8_t)b.filter; u.filter_param = b.filter_param;
-      if (has_check) { u.check = b.check_type; u.flags |= LZB_UNIT_VERIFY; u.expect = b.expect; }
-      post.push_back(u); post_block.push_back(k);
+      Post q;
+      memset(&q.u, 0, sizeof q.u);
+      q.block = k;
+      q.u.dst_off = w.units[b.first_unit].dst_off; q.u.dst_cap = (uint32_t)b.unpack_size;
+      if (b.n_units != 1) { q.u.filter = (uint8_t)b.filter; q.u.filter_param = b.filter_param; if (crc) q.u.check = b.check_type; }
+      post.push_back(q);
     }
   }
   std::vector<LzbResult> res(w.units.size());
-  SRes r = Lzb_DecodeUnitsHost(c, src, in_size, dest, cap, w.units.data(), res.data(), w.units.size());
+  SRes r = Lzb_DecodeUnitsHost(c, src, n, dest, cap, w.units.data(), res.data(), w.units.size());
   if (r != SZ_OK) return r;
 
-  /* stitch in stream order: the first failing unit / digest / padding decides */
-  uint64_t done = 0;
-  std::vector<SRes> block_res(w.blocks.size(), SZ_OK);
-  for (size_t k = 0; k < w.blocks.size(); k++)
+  /* which blocks came out clean */
+  std::vector<char> clean(nb, 1);
+  std::vector<uint64_t> digest(nb, 0);
+  for (size_t k = 0; k < nb; k++)
   {
     const LzbXzBlock &b = w.blocks[k];
     for (uint32_t j = 0; j < b.n_units; j++)
@@ -532,65 +540,87 @@ extern "C" SRes XzDecodeParallel(LzbContext *c, Byte *dest, SizeT *destLen, cons
       const LzbUnit &u = w.units[b.first_unit + j];
       const LzbResult &x = res[b.first_unit + j];
       const bool lastu = j + 1 == b.n_units;
-      done += x.dst_done;
-      bool clean;
-      if (b.complete && lastu) clean = x.res == SZ_OK && x.status == LZMA_STATUS_FINISHED_WITH_MARK;
-      else if (!lastu) clean = x.res == SZ_OK && x.dst_done == u.dst_cap && x.status != LZMA_STATUS_NEEDS_MORE_INPUT &&
-                               x.status != LZMA_STATUS_FINISHED_WITH_MARK;
-      else clean = false;                                /* cut-short block: its last unit ends the call */
-      if (!clean)
+      bool ok;
+      if (lastu) ok = x.res == SZ_OK && x.status == LZMA_STATUS_FINISHED_WITH_MARK && x.dst_done == u.dst_cap;
+      else ok = x.res == SZ_OK && x.dst_done == u.dst_cap && x.status != LZMA_STATUS_NEEDS_MORE_INPUT &&
+                x.status != LZMA_STATUS_FINISHED_WITH_MARK;
+      if (!ok) clean[k] = 0;
+    }
+    if (b.n_units == 1) digest[k] = res[b.first_unit].check;
+  }
+  std::vector<LzbShaJob> jobs;
+  std::vector<size_t> job_block;
+  if (!post.empty())
+  {
+    /* BCJ/Delta + digest over whole multi-unit blocks, SHA-256 over every block that asks for it */
+    std::vector<Post> live;
+    for (auto &q : post) if (clean[q.block]) live.push_back(q);
+    if (!live.empty())
+    {
+      std::lock_guard<std::mutex> g(c->mu);
+      LzbSlot &s = c->slot[0];
+      uint64_t lo = ~0ull, hi = 0;
+      for (auto &q : live) { lo = std::min<uint64_t>(lo, q.u.dst_off); hi = std::max<uint64_t>(hi, q.u.dst_off + q.u.dst_cap); }
+      if (hi <= lo) hi = lo + 1;
+      std::vector<LzbUnit> rel;
+      for (auto &q : live)
       {
-        *destLen = (size_t)done; *numBlocks = k;
-        if (x.res != SZ_OK) { *srcLen = (size_t)u.src_off + x.src_used; return x.res; }
-        *srcLen = in_size; *status = CODER_STATUS_NEEDS_MORE_INPUT;
-        return SZ_OK;
+        LzbUnit u = q.u; u.dst_off -= lo; rel.push_back(u);
+        if (w.blocks[q.block].check_type == LZB_CHECK_SHA256)
+        {
+          LzbShaJob j;
+          memset(&j, 0, sizeof j);
+          j.off = u.dst_off; j.len = u.dst_cap; j.finalize = 1;
+          lzb::sha256_init(j.state);
+          jobs.push_back(j); job_block.push_back(q.block);
+        }
+      }
+      const size_t job_bytes = jobs.size() * sizeof(LzbShaJob);
+      if (!lzb_slot_reserve(c, s, job_bytes + 16, (size_t)(hi - lo), rel.size(), 0)) return SZ_ERROR_MEM;
+      std::vector<LzbResult> pres(rel.size());
+      bool ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_out, dest + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s.stream), "H2D blocks") &&
+                lzb_cuda_ok(cudaMemcpyAsync(s.d_units, rel.data(), rel.size() * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D units");
+      if (!ok) return SZ_ERROR_FAIL;
+      int rc = lzb_launch_post_only(s.d_out, s.d_units, s.d_results, (uint32_t)rel.size(), s.stream);
+      if (rc != 0) { lzb_set_error("post launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+      if (!jobs.empty())
+      {
+        /* the job table rides in the (otherwise unused) packed staging area of the slot */
+        LzbShaJob *d_jobs = reinterpret_cast<LzbShaJob *>(s.d_packed);
+        ok = lzb_cuda_ok(cudaMemcpyAsync(d_jobs, jobs.data(), job_bytes, cudaMemcpyHostToDevice, s.stream), "H2D sha jobs");
+        if (!ok) return SZ_ERROR_FAIL;
+        rc = lzb_launch_sha256(s.d_out, d_jobs, (uint32_t)jobs.size(), s.stream);
+        if (rc != 0) { lzb_set_error("sha256 launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+        ok = lzb_cuda_ok(cudaMemcpyAsync(jobs.data(), d_jobs, job_bytes, cudaMemcpyDeviceToHost, s.stream), "D2H sha jobs");
+        if (!ok) return SZ_ERROR_FAIL;
+      }
+      for (size_t i = 0; i < live.size(); i++)
+        if (rel[i].filter != LZB_FILTER_NONE)
+          ok = ok && lzb_cuda_ok(cudaMemcpyAsync(dest + live[i].u.dst_off, s.d_out + rel[i].dst_off, rel[i].dst_cap, cudaMemcpyDeviceToHost, s.stream), "D2H blocks");
+      ok = ok && lzb_cuda_ok(cudaMemcpyAsync(pres.data(), s.d_results, pres.size() * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results") &&
+           lzb_cuda_ok(cudaStreamSynchronize(s.stream), "post kernel");
+      if (!ok) return SZ_ERROR_FAIL;
+      for (size_t i = 0; i < live.size(); i++)
+      {
+        if (pres[i].res != SZ_OK) clean[live[i].block] = 0;
+        if (w.blocks[live[i].block].n_units != 1) digest[live[i].block] = pres[i].check;
       }
     }
   }
-  if (!post.empty())
+  for (size_t k = 0; k < nb; k++)
   {
-    /* multi-unit blocks: BCJ/Delta + digest over the whole block, now that all of it is decoded */
-    std::vector<LzbResult> pres(post.size());
-    std::lock_guard<std::mutex> g(c->mu);
-    LzbSlot &s = c->slot[0];
-    uint64_t lo = ~0ull, hi = 0;
-    for (auto &u : post) { lo = std::min<uint64_t>(lo, u.dst_off); hi = std::max<uint64_t>(hi, u.dst_off + u.dst_cap); }
-    if (!lzb_slot_reserve(c, s, 0, (size_t)(hi - lo), post.size(), 0)) return SZ_ERROR_MEM;
-    std::vector<LzbUnit> rel = post;
-    for (auto &u : rel) u.dst_off -= lo;
-    bool ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_out, dest + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s.stream), "H2D blocks") &&
-              lzb_cuda_ok(cudaMemcpyAsync(s.d_units, rel.data(), rel.size() * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D units");
-    if (!ok) return SZ_ERROR_FAIL;
-    int rc = lzb_launch_post_only(s.d_out, s.d_units, s.d_results, (uint32_t)rel.size(), s.stream);
-    if (rc != 0) { lzb_set_error("post launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
-    for (auto &u : post)
-      ok = ok && lzb_cuda_ok(cudaMemcpyAsync(dest + u.dst_off, s.d_out + (u.dst_off - lo), u.dst_cap, cudaMemcpyDeviceToHost, s.stream), "D2H blocks");
-    ok = ok && lzb_cuda_ok(cudaMemcpyAsync(pres.data(), s.d_results, pres.size() * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results") &&
-         lzb_cuda_ok(cudaStreamSynchronize(s.stream), "post kernel");
-    if (!ok) return SZ_ERROR_FAIL;
-    for (size_t i = 0; i < post.size(); i++) block_res[post_block[i]] = pres[i].res;
-  }
-  done = 0;
-  for (size_t k = 0; k < w.blocks.size(); k++)
-  {
+    if (!clean[k]) continue;
     const LzbXzBlock &b = w.blocks[k];
-    if (b.complete == 0) break;
-    done += b.unpack_size;
-    SRes br = block_res[k];
-    if (b.n_units == 1 && res[b.first_unit].res != SZ_OK) br = res[b.first_unit].res;
-    if (w.after_block[k] != SZ_OK || (br != SZ_OK && b.complete == 1))
-    {
-      *destLen = (size_t)done; *numBlocks = k + 1;
-      *srcLen = (size_t)(b.complete == 1 ? b.check_off + XzFlags_GetCheckSize(b.check_type) : b.data_off + b.pack_size);
-      return w.after_block[k] != SZ_OK ? w.after_block[k] : br;
-    }
-    *numBlocks = k + 1;
+    XzReady q;
+    memset(&q, 0, sizeof q);
+    q.data_off = b.data_off; q.pack = b.pack_size; q.unpack = b.unpack_size;
+    q.dst_off = w.units[b.first_unit].dst_off;
+    q.check_type = b.check_type; q.n_filters = b.filter == LZB_FILTER_NONE ? 1 : 2;
+    q.digest = digest[k];
+    for (size_t i = 0; i < jobs.size(); i++) if (job_block[i] == k) memcpy(q.sha, jobs[i].digest, 32);
+    ready.push_back(q);
   }
-  *destLen = (size_t)done;
-  *srcLen = w.end_src;
-  *status = (ECoderStatus)w.end_status;
-  *streamFinished = w.finished ? 1 : 0;
-  return w.end_res;
+  return SZ_OK;
 }
 
 /* ------------------------------------------------------------------ xz backward index --------- */
@@ -609,13 +639,13 @@ extern "C" SRes Xz_ReadIndexBackward(const Byte *src, size_t srcLen, LzbXzBlock 
   const Byte *foot = src + end - 12;
   const unsigned flags = ((unsigned)foot[8] << 8) | foot[9];
   if (flags > 0xF) return SZ_ERROR_UNSUPPORTED;
-  if (lzb_le32(foot) != small_crc32(foot + 4, 6)) return SZ_ERROR_ARCHIVE;
+  if (lzb_le32(foot) != lzb_small_crc32(foot + 4, 6)) return SZ_ERROR_ARCHIVE;
   const size_t idx_size = ((size_t)lzb_le32(foot + 4) + 1) << 2;
   if (idx_size + 12 > end) return SZ_ERROR_NO_ARCHIVE;
   const size_t idx_off = end - 12 - idx_size;
   const Byte *idx = src + idx_off;
   if (idx_size < 5 || idx[0] != 0) return SZ_ERROR_ARCHIVE;
-  if (small_crc32(idx, idx_size - 4) != lzb_le32(idx + idx_size - 4)) return SZ_ERROR_ARCHIVE;
+  if (lzb_small_crc32(idx, idx_size - 4) != lzb_le32(idx + idx_size - 4)) return SZ_ERROR_ARCHIVE;
   size_t pos = 1;
   UInt64 v;
   unsigned s = Xz_ReadVarInt(idx + pos, idx_size - 4 - pos, &v);
@@ -656,11 +686,11 @@ extern "C" SRes Xz_ReadIndexBackward(const Byte *src, size_t srcLen, LzbXzBlock 
     if (src[cur] == 0) return SZ_ERROR_ARCHIVE;
     const UInt32 hs = ((UInt32)src[cur] << 2) + 4;
     if (hs + csz > total[i]) return SZ_ERROR_ARCHIVE;
-    XzFilterSpec fs[4];
-    int nf = 0;
-    r = parse_block_header(src + cur, fs, &nf);
+    CXzBlock blk;
+    memset(&blk, 0, sizeof blk);
+    r = XzBlock_Parse(&blk, src + cur);
     if (r != SZ_OK) return r;
-    r = classify_chain(fs, nf, &b);
+    r = lzb_xz_classify_chain(&blk, &b);
     if (r != SZ_OK) return r;
     b.hdr_off = cur; b.hdr_size = hs; b.data_off = cur + hs;
     b.pack_size = total[i] - hs - csz; b.unpack_size = unpack[i];
@@ -671,53 +701,4 @@ extern "C" SRes Xz_ReadIndexBackward(const Byte *src, size_t srcLen, LzbXzBlock 
     cur += (size_t)((total[i] + 3) & ~(UInt64)3);
   }
   return SZ_OK;
-}
-
-/* ------------------------------------------------------------------ XzUnpacker object --------- */
-struct XzUnpackerState
-{
-  uint64_t magic;
-  uint64_t num_blocks;
-  int finished;
-  int started;
-};
-#define XZU_MAGIC 0x4C5A42585A553031ull
-
-extern "C" SRes XzUnpacker_Create(CXzUnpacker *p, ISzAlloc *alloc)
-{
-  (void)alloc;
-  XzUnpackerState *s = (XzUnpackerState *)p;
-  memset(p, 0, sizeof *p);
-  s->magic = XZU_MAGIC;
-  return SZ_OK;
-}
-extern "C" void XzUnpacker_Free(CXzUnpacker *p) { (void)p; }
-extern "C" Bool XzUnpacker_IsStreamWasFinished(CXzUnpacker *p) { return ((XzUnpackerState *)p)->finished; }
-extern "C" UInt64 XzUnpacker_GetNumBlocks(const CXzUnpacker *p) { return ((const XzUnpackerState *)p)->num_blocks; }
-
-extern "C" SRes XzUnpacker_Code(CXzUnpacker *p, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
-                                int finishMode, ECoderStatus *status)
-{
-  (void)finishMode;
-  XzUnpackerState *s = (XzUnpackerState *)p;
-  if (s->magic != XZU_MAGIC) { *destLen = *srcLen = 0; return SZ_ERROR_PARAM; }
-  if (*srcLen == 0)
-  {
-    *destLen = 0;
-    *status = CODER_STATUS_NEEDS_MORE_INPUT;          /* reference XzDec.c:659-663 */
-    return SZ_OK;
-  }
-  if (s->started && !s->finished)
-  {
-    lzb_set_error("XzUnpacker_Code: resuming inside a stream is not supported in this round (present whole streams)");
-    *destLen = *srcLen = 0;
-    return SZ_ERROR_UNSUPPORTED;
-  }
-  UInt64 nb = 0;
-  int fin = 0;
-  SRes r = XzDecodeParallel(nullptr, dest, destLen, src, srcLen, status, &nb, &fin);
-  s->started = 1;
-  s->num_blocks += nb;
-  s->finished = fin;
-  return r;
 }

@@ -878,6 +878,7 @@ template <uint32_t G> struct UnitDecoderT
     {
       /* resume: CLzmaDec / CLzma2Dec as the previous call left them (host keeps the scalars authoritative) */
       load_state(sst);
+      held_out = sst->held;
       if (!raw)
       {
         phase = (int)sst->l2_phase; control = sst->l2_control;
@@ -901,6 +902,11 @@ template <uint32_t G> struct UnitDecoderT
    *   S_TD_RET     back in Lzma2Dec_DecodeToDic after the call (Lzma2Dec.c:264-284)                      */
   LZB_FN void advance()
   {
+    /* Resuming with bytes the previous call had parked (CLzmaDec.tempBuf): the reference decodes exactly ONE
+     * symbol out of tempBuf and commits it before it goes back to the caller's buffer (LzmaDec.c:804-833).
+     * The bytes are contiguous here, but that commit point is observable when a later symbol of the same
+     * call fails (srcLen / destLen of the failing call), so the first run is cut after one symbol too. */
+    bool one_symbol_run = false;
     for (;;)
     {
       switch (st)
@@ -998,6 +1004,7 @@ template <uint32_t G> struct UnitDecoderT
         case S_TD_ENTER:
           ctx_stale = false;
           td_used = 0;
+          one_symbol_run = held_out != 0 && !want_rc_init;      /* held_out still holds what the last call parked */
           held_out = 0;
           if (!want_rc_init) { rc_seek(td_src); ctx_stale = true; }     /* continuing a chunk / a suspended stream */
           flush_pending(td_limit);
@@ -1056,7 +1063,8 @@ template <uint32_t G> struct UnitDecoderT
             run_soft = td_src;
           }
           else
-            run_soft = td_src + td_avail - kLookahead;
+            run_soft = one_symbol_run ? td_src : td_src + td_avail - kLookahead;
+          one_symbol_run = false;
           st = S_SPAN_TOP;
           continue;
         }

@@ -605,6 +605,19 @@ extern "C" SizeT x86_Convert(Byte *data, SizeT size, UInt32 ip, UInt32 *state, i
 
 extern "C" void Delta_Init(Byte *state) { memset(state, 0, DELTA_STATE_SIZE); }
 
+extern "C" void Delta_Encode(Byte *state, unsigned delta, Byte *data, SizeT size)
+{
+  /* reference Delta.c:20-41.  The GPU pass takes a zero history; the incoming one only touches the first
+   * `delta` bytes (out[i] = in[i] - hist[i]); the outgoing history is the last `delta` INPUT bytes. */
+  if (size == 0) return;
+  Byte next[DELTA_STATE_SIZE];
+  if (size >= delta) memcpy(next, data + size - delta, delta);
+  else { memcpy(next, state + size, delta - size); memcpy(next + delta - size, data, size); }
+  if (!gpu_filter(data, size, LZB_FILTER_DELTA, delta, 2)) return;
+  for (unsigned i = 0; i < delta && i < size; i++) data[i] = (Byte)(data[i] - state[i]);
+  memcpy(state, next, delta);
+}
+
 extern "C" void Delta_Decode(Byte *state, unsigned delta, Byte *data, SizeT size)
 {
   /* reference Delta.c:43-62.  A non-zero incoming history is folded in on the host (it only affects

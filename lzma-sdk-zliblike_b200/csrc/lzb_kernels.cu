@@ -19,6 +19,7 @@
 
 #include "lzb_core.cuh"
 #include "lzb_post.cuh"
+#include "lzb_sha256.cuh"
 #include "lzb_kernels.h"
 
 namespace lzb {
@@ -107,6 +108,21 @@ lzb_post_only_kernel(uint8_t *__restrict__ data, const LzbUnit *__restrict__ uni
   r.res = LZB_SZ_OK; r.status = LZB_ST_NOT_SPECIFIED; r.src_used = 0; r.dst_done = u.dst_cap; r.check = 0;
   post_process<32>(u, r, data + u.dst_off, scratch[warp], scratch[warp]);
   if (lane == 0) results[i] = r;
+}
+
+/* xz block check 10 (SHA-256, Xz.c:45-88): a digest is one serial chain, so one thread per job; blocks of
+ * an xz file are independent jobs.  Not fused into the decode kernel: it would grow the hot kernel's code
+ * and registers for a check the reference's own encoder never selects by default. */
+__global__ void __launch_bounds__(32)
+lzb_sha256_kernel(const uint8_t *__restrict__ data, LzbShaJob *jobs, uint32_t n_jobs)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_jobs) return;
+  LzbShaJob j = jobs[i];
+  const uint8_t *p = data + j.off;
+  if (j.finalize) sha256_finish(j.state, p, j.len, j.before, j.digest);
+  else for (uint64_t k = 0; k + 64 <= j.len; k += 64) sha256_block(j.state, p + k);
+  jobs[i] = j;
 }
 
 }  // namespace lzb
@@ -241,5 +257,12 @@ extern "C" int lzb_launch_post_only(uint8_t *d_data, const LzbUnit *d_units, Lzb
   if (n_units == 0) return 0;
   const uint32_t warps = 4;
   lzb::lzb_post_only_kernel<<<(n_units + warps - 1) / warps, warps * 32, 0, stream>>>(d_data, d_units, d_results, n_units);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int lzb_launch_sha256(const uint8_t *d_data, LzbShaJob *d_jobs, uint32_t n_jobs, cudaStream_t stream)
+{
+  if (n_jobs == 0) return 0;
+  lzb::lzb_sha256_kernel<<<(n_jobs + 31) / 32, 32, 0, stream>>>(d_data, d_jobs, n_jobs);
   return (int)cudaGetLastError();
 }

@@ -258,6 +258,30 @@ template <uint32_t G> LZB_FN uint64_t crc64_group(const uint8_t *data, uint32_t 
   return ~v;
 }
 
+/* Delta_Encode (Delta.c:20-41), zero incoming history: out[i] = in[i] - in[i-d].  In place: chunks of G bytes
+ * from the top down, every chunk read completely before it is written (out[i] needs in[i-d], below it). */
+template <uint32_t G> LZB_FN void delta_encode_group(uint8_t *data, uint32_t n, uint32_t d)
+{
+  typedef Group<G> Grp;
+  uint32_t top = n;
+  while (top > 0)
+  {
+    const uint32_t base = top > G ? top - G : 0;
+    const uint32_t i = base + Grp::lane();
+    const bool on = i < top;
+    uint8_t v = 0;
+    if (on)
+    {
+      v = data[i];
+      if (i >= d) v = (uint8_t)(v - data[i - d]);
+    }
+    Grp::sync();
+    if (on) data[i] = v;
+    Grp::sync();
+    top = base;
+  }
+}
+
 /* filter -> check -> verdict, for one decoded unit.
  * `scratch`     : >= kPostSmemBytes of the group's (dead) shared-memory model region -- CRC table.
  * `big_scratch` : >= kPostScratchBytes, the group's (dead) matched-literal slab slice in HBM/L2 -- Delta
@@ -273,7 +297,11 @@ template <uint32_t G> LZB_FN void post_process(const LzbUnit &u, LzbResult &r, u
     const uint32_t done = x86_convert_group<G>(data, n, u.filter_param, (u.flags & 2) != 0, st);
     if (u.flags & 4) { r.src_used = done; r.status = (int32_t)st; }   /* stand-alone call: report them */
   }
-  else if (u.filter == LZB_FILTER_DELTA) delta_decode_group<G>(data, n, u.filter_param, big_scratch);
+  else if (u.filter == LZB_FILTER_DELTA)
+  {
+    if (u.flags & 2) delta_encode_group<G>(data, n, u.filter_param);   /* stand-alone Delta_Encode call */
+    else delta_decode_group<G>(data, n, u.filter_param, big_scratch);
+  }
   if (u.check == LZB_CHECK_CRC32) r.check = crc32_group<G>(data, n, reinterpret_cast<uint32_t *>(scratch));
   else if (u.check == LZB_CHECK_CRC64) r.check = crc64_group<G>(data, n, reinterpret_cast<uint64_t *>(scratch));
   if ((u.flags & LZB_UNIT_VERIFY) && u.check != LZB_CHECK_NONE && r.check != u.expect) r.res = LZB_SZ_ERROR_CRC;

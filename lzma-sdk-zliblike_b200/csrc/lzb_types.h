@@ -15,7 +15,7 @@ extern "C" {
 
 enum { LZB_CODEC_LZMA = 0, LZB_CODEC_LZMA2 = 1 };
 enum { LZB_FILTER_NONE = 0, LZB_FILTER_DELTA = 3, LZB_FILTER_X86 = 4 };   /* xz filter ids, Xz.h:11-19 */
-enum { LZB_CHECK_NONE = 0, LZB_CHECK_CRC32 = 1, LZB_CHECK_CRC64 = 4 };     /* xz check ids, Xz.h:66-69 */
+enum { LZB_CHECK_NONE = 0, LZB_CHECK_CRC32 = 1, LZB_CHECK_CRC64 = 4, LZB_CHECK_SHA256 = 10 };   /* xz check ids, Xz.h:66-69 */
 enum
 {
   LZB_UNIT_VERIFY = 1,       /* compare the computed digest with `expect` -> SZ_ERROR_CRC              */
@@ -113,6 +113,17 @@ static inline uint32_t lzb_gmem_probs(unsigned lc, unsigned lp)
 {
   return 512u << (lc + lp);
 }
+
+/* One SHA-256 job of lzb_sha256_kernel (xz block check 10, Xz.c:45-88): hash `len` bytes at data + off.
+ * finalize = 0: len is a multiple of 64, `state` is updated in place (Sha256_Update of whole blocks);
+ * finalize = 1: the message ends here (`before` bytes were hashed into `state` earlier), digest is written. */
+typedef struct LzbShaJob
+{
+  uint64_t off, len, before;
+  uint32_t state[8];
+  uint32_t finalize, pad_;
+  uint8_t digest[32];
+} LzbShaJob;
 
 #ifdef __cplusplus
 }

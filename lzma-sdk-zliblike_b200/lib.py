@@ -27,7 +27,7 @@ def declared_symbols() -> list[str]:
     txt = "\n".join(l for l in txt.splitlines() if not l.strip().startswith("#"))
     names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", txt))
     names |= set(re.findall(r"extern\s+\w+\s+(\w+)\[\]", txt))
-    names -= {"Alloc", "Free", "sizeof"}
+    names -= {"Alloc", "Free", "sizeof", "SRes", "void"}      # function-pointer fields, keywords
     return sorted(n for n in names if not n.startswith("_"))
 
 

@@ -3,6 +3,7 @@ include/lzb200.h declares, keeps the reference's public struct layouts, refuses 
 device (no CPU fallback), and its HOST-side front ends (property parsing, LZMA2 unit walk, xz index and
 varints) agree with the oracle.  No compute call is made here."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -46,8 +47,24 @@ def test_public_struct_layouts_match_reference_abi():
                         processedPos=64, checkDicSize=68, state=72, reps=76, remainLen=92, needFlush=96,
                         needInitState=100, numProbs=104, tempBufSize=108, tempBuf=112)
     assert CLzma2Dec.packSize.offset == 136 and CLzma2Dec.needInitProp.offset == 160
-    hdr = open(L.HEADER).read()
-    assert "UInt64 opaque[224]" in hdr           # CXzUnpacker storage = 1792 bytes like the reference's
+    # the xz objects: compile the public header as C and ask the compiler
+    import subprocess, tempfile
+    prog = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "lzb200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(CXzUnpacker), sizeof(CMixCoder), sizeof(CXzBlock),
+         sizeof(CXzCheck), sizeof(IStateCoder), sizeof(CSha256), offsetof(CXzUnpacker, numBlocks),
+         offsetof(CXzUnpacker, decoder), offsetof(CXzUnpacker, buf));
+  return 0; }
+"""
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, "abi.c"), os.path.join(td, "abi")
+        open(src, "w").write(prog)
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.dirname(L.HEADER), src, "-o", exe])
+        got = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert got == [1792, 272, 152, 120, 40, 104, 40, 88, 768], got       # = the reference build (gcc, x86-64; SURVEY.md §8b)
     assert R.UNIT_DTYPE.itemsize == 48 and R.RESULT_DTYPE.itemsize == 24
 
 

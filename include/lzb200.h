@@ -163,6 +163,11 @@ UInt64 Crc64Calc(const void *data, size_t size);
 /* ---- post-filters: reference Bra.h:56-58, Delta.h:13-17 ---- */
 #define x86_Convert_Init(state) { state = 0; }
 SizeT x86_Convert(Byte *data, SizeT size, UInt32 ip, UInt32 *state, int encoding);
+SizeT ARM_Convert(Byte *data, SizeT size, UInt32 ip, int encoding);      /* Bra.h:59-63; stateless, elementwise */
+SizeT ARMT_Convert(Byte *data, SizeT size, UInt32 ip, int encoding);
+SizeT PPC_Convert(Byte *data, SizeT size, UInt32 ip, int encoding);
+SizeT SPARC_Convert(Byte *data, SizeT size, UInt32 ip, int encoding);
+SizeT IA64_Convert(Byte *data, SizeT size, UInt32 ip, int encoding);
 #define DELTA_STATE_SIZE 256
 void Delta_Init(Byte *state);
 void Delta_Encode(Byte *state, unsigned delta, Byte *data, SizeT size);
@@ -238,9 +243,9 @@ typedef struct
   IStateCoder coders[MIXCODER_NUM_FILTERS_MAX];
 } CMixCoder;
 
-/* The resumable filter chain of an xz block (XzDec.c:356-480): LZMA2 first (stateful, on the GPU), then
- * x86 BCJ / Delta over a 16 KiB staging buffer exactly as BraState_Code does.  The other branch converters
- * (PPC, IA64, ARM, ARMT, SPARC) are not on the hot path: SetFromMethod returns SZ_ERROR_UNSUPPORTED. */
+/* The resumable filter chain of an xz block (XzDec.c:356-480): LZMA2 first (stateful, on the GPU), then a
+ * branch converter (x86, PPC, IA64, ARM, ARMT, SPARC) or Delta over a 16 KiB staging buffer exactly as
+ * BraState_Code does. */
 void MixCoder_Construct(CMixCoder *p, ISzAlloc *alloc);
 void MixCoder_Free(CMixCoder *p);
 void MixCoder_Init(CMixCoder *p);

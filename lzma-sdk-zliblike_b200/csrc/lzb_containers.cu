@@ -306,7 +306,18 @@ SRes lzb_xz_classify_chain(const CXzBlock *blk, LzbXzBlock *b)
     b->filter = LZB_FILTER_X86;
     return SZ_OK;
   }
-  lzb_set_error("xz filter id %llu is outside the GPU hot path", (unsigned long long)f[0].id);
+  if (f[0].id >= XZ_ID_PPC && f[0].id <= XZ_ID_SPARC)
+  {
+    /* stateless RISC converters; start-offset alignment rules of BraState_SetProps (XzDec.c:84-104) */
+    UInt32 v = 0;
+    if (f[0].propsSize == 4) v = lzb_le32(f[0].props);
+    else if (f[0].propsSize != 0) return SZ_ERROR_UNSUPPORTED;
+    const UInt32 need = f[0].id == XZ_ID_IA64 ? 15u : (f[0].id == XZ_ID_ARMT ? 1u : 3u);
+    if (v & need) return SZ_ERROR_UNSUPPORTED;
+    b->filter = (int32_t)f[0].id; b->filter_param = v;
+    return SZ_OK;
+  }
+  lzb_set_error("xz filter id %llu is not a filter of the reference", (unsigned long long)f[0].id);
   return SZ_ERROR_UNSUPPORTED;
 }
 
@@ -507,21 +518,21 @@ SRes lzb_xz_prefetch(LzbContext *c, const Byte *src, size_t n, bool in_blocks, u
     const bool crc = b.check_type == LZB_CHECK_CRC32 || b.check_type == LZB_CHECK_CRC64;
     const bool sha = b.check_type == LZB_CHECK_SHA256;
     if (b.filter == LZB_FILTER_NONE && !crc && !sha) continue;
-    bool second = sha;
-    if (b.n_units == 1)
+    /* the decode kernel fuses x86 / Delta + CRC for one-unit blocks; everything else is a second pass */
+    const bool fused = b.n_units == 1 && (b.filter == LZB_FILTER_NONE || b.filter == LZB_FILTER_X86 || b.filter == LZB_FILTER_DELTA);
+    if (fused)
     {
       LzbUnit &u = w.units[b.first_unit];
       u.filter = (uint8_t)b.filter; u.filter_param = b.filter_param;
       if (crc) u.check = b.check_type;
     }
-    else second = true;
-    if (second)
+    if (!fused || sha)
     {
       Post q;
       memset(&q.u, 0, sizeof q.u);
       q.block = k;
       q.u.dst_off = w.units[b.first_unit].dst_off; q.u.dst_cap = (uint32_t)b.unpack_size;
-      if (b.n_units != 1) { q.u.filter = (uint8_t)b.filter; q.u.filter_param = b.filter_param; if (crc) q.u.check = b.check_type; }
+      if (!fused) { q.u.filter = (uint8_t)b.filter; q.u.filter_param = b.filter_param; if (crc) q.u.check = b.check_type; }
       post.push_back(q);
     }
   }
@@ -546,7 +557,7 @@ SRes lzb_xz_prefetch(LzbContext *c, const Byte *src, size_t n, bool in_blocks, u
                 x.status != LZMA_STATUS_FINISHED_WITH_MARK;
       if (!ok) clean[k] = 0;
     }
-    if (b.n_units == 1) digest[k] = res[b.first_unit].check;
+    digest[k] = res[b.first_unit].check;      /* fused one-unit blocks; overwritten by the second pass otherwise */
   }
   std::vector<LzbShaJob> jobs;
   std::vector<size_t> job_block;
@@ -603,7 +614,7 @@ SRes lzb_xz_prefetch(LzbContext *c, const Byte *src, size_t n, bool in_blocks, u
       for (size_t i = 0; i < live.size(); i++)
       {
         if (pres[i].res != SZ_OK) clean[live[i].block] = 0;
-        if (w.blocks[live[i].block].n_units != 1) digest[live[i].block] = pres[i].check;
+        if (rel[i].check != LZB_CHECK_NONE) digest[live[i].block] = pres[i].check;
       }
     }
   }

@@ -603,6 +603,20 @@ extern "C" SizeT x86_Convert(Byte *data, SizeT size, UInt32 ip, UInt32 *state, i
   return r.src_used;
 }
 
+/* reference Bra.c:6-133, BraIA64.c:16-69: stateless, one aligned instruction slot per GPU thread */
+static SizeT risc_convert(int filter, Byte *data, SizeT size, UInt32 ip, int encoding, SizeT min_size)
+{
+  if (size < min_size) return 0;
+  LzbResult r;
+  if (!gpu_filter(data, size, filter, ip, (uint8_t)(4 | (encoding ? 2 : 0)), 0, &r)) return 0;
+  return r.src_used;
+}
+extern "C" SizeT ARM_Convert(Byte *data, SizeT size, UInt32 ip, int encoding) { return risc_convert(LZB_FILTER_ARM, data, size, ip, encoding, 4); }
+extern "C" SizeT ARMT_Convert(Byte *data, SizeT size, UInt32 ip, int encoding) { return risc_convert(LZB_FILTER_ARMT, data, size, ip, encoding, 4); }
+extern "C" SizeT PPC_Convert(Byte *data, SizeT size, UInt32 ip, int encoding) { return risc_convert(LZB_FILTER_PPC, data, size, ip, encoding, 4); }
+extern "C" SizeT SPARC_Convert(Byte *data, SizeT size, UInt32 ip, int encoding) { return risc_convert(LZB_FILTER_SPARC, data, size, ip, encoding, 4); }
+extern "C" SizeT IA64_Convert(Byte *data, SizeT size, UInt32 ip, int encoding) { return risc_convert(LZB_FILTER_IA64, data, size, ip, encoding, 16); }
+
 extern "C" void Delta_Init(Byte *state) { memset(state, 0, DELTA_STATE_SIZE); }
 
 extern "C" void Delta_Encode(Byte *state, unsigned delta, Byte *data, SizeT size)

@@ -106,7 +106,7 @@ lzb_post_only_kernel(uint8_t *__restrict__ data, const LzbUnit *__restrict__ uni
   const LzbUnit u = units[i];
   LzbResult r;
   r.res = LZB_SZ_OK; r.status = LZB_ST_NOT_SPECIFIED; r.src_used = 0; r.dst_done = u.dst_cap; r.check = 0;
-  post_process<32>(u, r, data + u.dst_off, scratch[warp], scratch[warp]);
+  post_process<32, true>(u, r, data + u.dst_off, scratch[warp], scratch[warp]);
   if (lane == 0) results[i] = r;
 }
 

@@ -258,6 +258,102 @@ template <uint32_t G> LZB_FN uint64_t crc64_group(const uint8_t *data, uint32_t 
   return ~v;
 }
 
+/* ------------------------------------------------------------------ RISC branch converters ----- */
+/* ARM, ARMT, PPC, SPARC (Bra.c:6-133) and IA64 (BraIA64.c:16-69) rewrite one aligned instruction slot at a
+ * time and carry no state, so every slot is an independent job: lanes take slots round-robin.  (ARMT looks
+ * sequential -- a converted pair skips the next halfword -- but a BL pair at i and one at i+2 would need
+ * byte i+3 to be both 11110xxx and 11111xxx, and conversion keeps those bits: candidates never overlap.)
+ * Each returns what the reference's loop counter returns: the bytes it is done with. */
+LZB_FN uint32_t bra_rel(uint32_t v, uint32_t pc, bool encoding) { return encoding ? pc + v : v - pc; }
+
+template <uint32_t G> LZB_FN uint32_t risc_convert_group(uint8_t *d, uint32_t size, uint32_t filter, uint32_t ip, bool enc)
+{
+  typedef Group<G> Grp;
+  const uint32_t lane = Grp::lane();
+  Grp::sync();
+  if (filter == LZB_FILTER_IA64)
+  {
+    if (size < 16) return 0;
+    const uint32_t n = size >> 4;
+    for (uint32_t b = lane; b < n; b += G)
+    {
+      uint8_t *q = d + ((size_t)b << 4);
+      const uint32_t tmpl = q[0] & 0x1F;
+      /* kBranchTable (BraIA64.c:6-12): templates 16,17,24,25,28,29 -> slot 2; 18,19 -> slots 1,2; 22,23 -> all */
+      const uint32_t mask = (tmpl == 16 || tmpl == 17 || tmpl == 24 || tmpl == 25 || tmpl == 28 || tmpl == 29) ? 4u
+                          : ((tmpl == 18 || tmpl == 19) ? 6u : ((tmpl == 22 || tmpl == 23) ? 7u : 0u));
+      for (uint32_t slot = 0, bit = 5; slot < 3; slot++, bit += 41)
+      {
+        if (((mask >> slot) & 1) == 0) continue;
+        const uint32_t at = bit >> 3, sh = bit & 7;
+        uint64_t ins = 0;
+        for (int j = 0; j < 6; j++) ins += (uint64_t)q[at + j] << (8 * j);
+        uint64_t norm = ins >> sh;
+        if (((norm >> 37) & 0xF) != 0x5 || ((norm >> 9) & 0x7) != 0) continue;
+        uint32_t v = (uint32_t)((norm >> 13) & 0xFFFFF) | (((uint32_t)(norm >> 36) & 1) << 20);
+        v = bra_rel(v << 4, ip + (b << 4), enc) >> 4;
+        norm &= ~((uint64_t)0x8FFFFF << 13);
+        norm |= (uint64_t)(v & 0xFFFFF) << 13;
+        norm |= (uint64_t)(v & 0x100000) << (36 - 20);
+        ins = (ins & ((1u << sh) - 1)) | (norm << sh);
+        for (int j = 0; j < 6; j++) q[at + j] = (uint8_t)(ins >> (8 * j));
+      }
+    }
+    Grp::sync();
+    return n << 4;
+  }
+  if (size < 4) return 0;
+  if (filter == LZB_FILTER_ARMT)
+  {
+    const uint32_t last = (size - 4) & ~1u;               /* last halfword position the loop can look at */
+    bool hit_last = false;
+    for (uint32_t i = lane * 2; i <= last; i += G * 2)
+    {
+      uint8_t *q = d + i;
+      if ((q[1] & 0xF8) != 0xF0 || (q[3] & 0xF8) != 0xF8) continue;
+      uint32_t v = (((uint32_t)q[1] & 7) << 19) | ((uint32_t)q[0] << 11) | (((uint32_t)q[3] & 7) << 8) | q[2];
+      v = bra_rel(v << 1, ip + 4 + i, enc) >> 1;
+      q[1] = (uint8_t)(0xF0 | ((v >> 19) & 7)); q[0] = (uint8_t)(v >> 11);
+      q[3] = (uint8_t)(0xF8 | ((v >> 8) & 7));  q[2] = (uint8_t)v;
+      if (i == last) hit_last = true;
+    }
+    const bool any = Grp::ballot(hit_last) != 0;
+    Grp::sync();
+    return last + (any ? 4u : 2u);
+  }
+  const uint32_t n = size >> 2;
+  for (uint32_t w = lane; w < n; w += G)
+  {
+    uint8_t *q = d + ((size_t)w << 2);
+    const uint32_t i = w << 2;
+    if (filter == LZB_FILTER_ARM)
+    {
+      if (q[3] != 0xEB) continue;
+      uint32_t v = ((uint32_t)q[2] << 16) | ((uint32_t)q[1] << 8) | q[0];
+      v = bra_rel(v << 2, ip + 8 + i, enc) >> 2;
+      q[2] = (uint8_t)(v >> 16); q[1] = (uint8_t)(v >> 8); q[0] = (uint8_t)v;
+    }
+    else if (filter == LZB_FILTER_PPC)
+    {
+      if ((q[0] >> 2) != 0x12 || (q[3] & 3) != 1) continue;
+      uint32_t v = ((uint32_t)(q[0] & 3) << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (q[3] & ~3u);
+      v = bra_rel(v, ip + i, enc);
+      q[0] = (uint8_t)(0x48 | ((v >> 24) & 3)); q[1] = (uint8_t)(v >> 16); q[2] = (uint8_t)(v >> 8);
+      q[3] = (uint8_t)((q[3] & 3) | v);
+    }
+    else /* SPARC */
+    {
+      if (!((q[0] == 0x40 && (q[1] & 0xC0) == 0x00) || (q[0] == 0x7F && (q[1] & 0xC0) == 0xC0))) continue;
+      uint32_t v = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+      v = bra_rel(v << 2, ip + i, enc) >> 2;
+      v = (((0u - ((v >> 22) & 1)) << 22) & 0x3FFFFFFFu) | (v & 0x3FFFFFu) | 0x40000000u;
+      q[0] = (uint8_t)(v >> 24); q[1] = (uint8_t)(v >> 16); q[2] = (uint8_t)(v >> 8); q[3] = (uint8_t)v;
+    }
+  }
+  Grp::sync();
+  return n << 2;
+}
+
 /* Delta_Encode (Delta.c:20-41), zero incoming history: out[i] = in[i] - in[i-d].  In place: chunks of G bytes
  * from the top down, every chunk read completely before it is written (out[i] needs in[i-d], below it). */
 template <uint32_t G> LZB_FN void delta_encode_group(uint8_t *data, uint32_t n, uint32_t d)
@@ -286,7 +382,10 @@ template <uint32_t G> LZB_FN void delta_encode_group(uint8_t *data, uint32_t n, 
  * `scratch`     : >= kPostSmemBytes of the group's (dead) shared-memory model region -- CRC table.
  * `big_scratch` : >= kPostScratchBytes, the group's (dead) matched-literal slab slice in HBM/L2 -- Delta
  *                 column sums (up to 256 x G bytes; Delta blocks are rare, L2 latency is acceptable). */
-template <uint32_t G> LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t *scratch, uint8_t *big_scratch)
+/* kRisc: also the stateless RISC converters (only the stand-alone / second-pass kernel carries them, the
+ * fused decode kernel stays lean: BCJ x86 and Delta are what the reference's own writers emit). */
+template <uint32_t G, bool kRisc = false>
+LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t *scratch, uint8_t *big_scratch)
 {
   if (r.res != LZB_SZ_OK) return;
   const uint32_t n = r.dst_done;
@@ -301,6 +400,11 @@ template <uint32_t G> LZB_FN void post_process(const LzbUnit &u, LzbResult &r, u
   {
     if (u.flags & 2) delta_encode_group<G>(data, n, u.filter_param);   /* stand-alone Delta_Encode call */
     else delta_decode_group<G>(data, n, u.filter_param, big_scratch);
+  }
+  else if (kRisc && u.filter >= LZB_FILTER_PPC && u.filter <= LZB_FILTER_SPARC)
+  {
+    const uint32_t done = risc_convert_group<G>(data, n, u.filter, u.filter_param, (u.flags & 2) != 0);
+    if (u.flags & 4) r.src_used = done;
   }
   if (u.check == LZB_CHECK_CRC32) r.check = crc32_group<G>(data, n, reinterpret_cast<uint32_t *>(scratch));
   else if (u.check == LZB_CHECK_CRC64) r.check = crc64_group<G>(data, n, reinterpret_cast<uint64_t *>(scratch));

@@ -14,7 +14,8 @@ extern "C" {
 #endif
 
 enum { LZB_CODEC_LZMA = 0, LZB_CODEC_LZMA2 = 1 };
-enum { LZB_FILTER_NONE = 0, LZB_FILTER_DELTA = 3, LZB_FILTER_X86 = 4 };   /* xz filter ids, Xz.h:11-19 */
+enum { LZB_FILTER_NONE = 0, LZB_FILTER_DELTA = 3, LZB_FILTER_X86 = 4, LZB_FILTER_PPC = 5, LZB_FILTER_IA64 = 6,
+       LZB_FILTER_ARM = 7, LZB_FILTER_ARMT = 8, LZB_FILTER_SPARC = 9 };        /* xz filter ids, Xz.h:11-19 */
 enum { LZB_CHECK_NONE = 0, LZB_CHECK_CRC32 = 1, LZB_CHECK_CRC64 = 4, LZB_CHECK_SHA256 = 10 };   /* xz check ids, Xz.h:66-69 */
 enum
 {

@@ -167,7 +167,13 @@ static SRes bra_set_props(void *pp, const Byte *props, size_t propSize, ISzAlloc
     b->delta = (UInt32)props[0] + 1;
     return SZ_OK;
   }
-  if (propSize == 4) b->ip = lzb_le32(props);
+  if (propSize == 4)
+  {
+    const UInt32 v = lzb_le32(props);
+    const UInt32 need = b->method == XZ_ID_X86 ? 0u : (b->method == XZ_ID_IA64 ? 15u : (b->method == XZ_ID_ARMT ? 1u : 3u));
+    if (v & need) return SZ_ERROR_UNSUPPORTED;
+    b->ip = v;
+  }
   else if (propSize != 0) return SZ_ERROR_UNSUPPORTED;
   return SZ_OK;
 }
@@ -213,8 +219,12 @@ static SRes bra_code(void *pp, Byte *dest, SizeT *destLen, const Byte *src, Size
       else Delta_Decode(b->delta_state, b->delta, b->buf, b->held);
       b->converted = b->held;
     }
-    else if (b->method == XZ_ID_X86)
-      b->converted = x86_Convert(b->buf, b->held, b->ip, &b->x86_state, b->encode);
+    else if (b->method == XZ_ID_X86) b->converted = x86_Convert(b->buf, b->held, b->ip, &b->x86_state, b->encode);
+    else if (b->method == XZ_ID_PPC) b->converted = PPC_Convert(b->buf, b->held, b->ip, b->encode);
+    else if (b->method == XZ_ID_IA64) b->converted = IA64_Convert(b->buf, b->held, b->ip, b->encode);
+    else if (b->method == XZ_ID_ARM) b->converted = ARM_Convert(b->buf, b->held, b->ip, b->encode);
+    else if (b->method == XZ_ID_ARMT) b->converted = ARMT_Convert(b->buf, b->held, b->ip, b->encode);
+    else if (b->method == XZ_ID_SPARC) b->converted = SPARC_Convert(b->buf, b->held, b->ip, b->encode);
     else
       return SZ_ERROR_UNSUPPORTED;
     b->ip += (UInt32)b->converted;
@@ -230,13 +240,8 @@ static SRes bra_code(void *pp, Byte *dest, SizeT *destLen, const Byte *src, Size
 
 static SRes bra_attach(IStateCoder *sc, UInt64 id, ISzAlloc *alloc)
 {
-  /* the reference also accepts PPC / IA64 / ARM / ARMT / SPARC here (XzDec.c:198-221); those converters are
-   * outside this library's path */
-  if (id != XZ_ID_Delta && id != XZ_ID_X86)
-  {
-    lzb_set_error("xz filter id %llu is outside the GPU hot path", (unsigned long long)id);
-    return SZ_ERROR_UNSUPPORTED;
-  }
+  /* XzDec.c:198-221 */
+  if (id != XZ_ID_Delta && (id < XZ_ID_X86 || id > XZ_ID_SPARC)) return SZ_ERROR_UNSUPPORTED;
   sc->p = 0;
   BraStage *b = (BraStage *)alloc->Alloc(alloc, sizeof(BraStage));
   if (!b) return SZ_ERROR_MEM;

@@ -145,6 +145,27 @@ def delta_decode(data, dist: int, state=None):
     return buf, st
 
 
+def delta_encode(data, dist: int, state=None):
+    """Delta_Encode (reference Delta.h:16): returns (bytes, state)."""
+    buf = _u8(data).copy()
+    st = np.zeros(256, dtype=np.uint8) if state is None else _u8(state).copy()
+    _lib.load().Delta_Encode(_p(st), dist, _p(buf), len(buf))
+    return buf, st
+
+
+_BRA = {5: "PPC_Convert", 6: "IA64_Convert", 7: "ARM_Convert", 8: "ARMT_Convert", 9: "SPARC_Convert"}
+
+
+def bra_convert(filter_id: int, data, ip: int = 0, encoding: int = 0):
+    """ARM/ARMT/PPC/SPARC/IA64_Convert (reference Bra.h:59-63) by xz filter id: returns (bytes, processed)."""
+    buf = _u8(data).copy()
+    f = getattr(_lib.load(), _BRA[filter_id])
+    f.restype = C.c_size_t
+    f.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int]
+    n = f(_p(buf), len(buf), ip, encoding)
+    return buf, int(n)
+
+
 # ----------------------------------------------------------------------------- units (batched extension)
 def decode_units_host(ctx, packed: np.ndarray, out: np.ndarray, units: np.ndarray) -> np.ndarray:
     """Lzb_DecodeUnitsHost over numpy arenas (pinned or pageable)."""

@@ -9,6 +9,7 @@
  *                                  which skips Lzma2Dec_Init -- Lzma2Dec.c:330-356)
  *   - zlib-like buffer interface : LzmaUtil.c:55-106 pattern
  *   - xz container               : XzEnc.c:41-160 writers + XzDec.c:604 unpacker
+ *   - 7z archive                 : SzArEx_Open + SzArEx_Extract per file (7zIn.c:1314-1405)
  *   - pthread "one unit per core" decode loop = the CPU baseline of BASELINE.md §2
  *
  * Used by: tests/ (differential pinning of oracle/ and of the CUDA path),
@@ -23,7 +24,9 @@
 #include <string.h>
 #include <time.h>
 
+#include "7z.h"
 #include "7zCrc.h"
+#include "7zStream.h"
 #include "Alloc.h"
 #include "Bra.h"
 #include "Delta.h"
@@ -546,6 +549,18 @@ void refh_x86_filter_whole(uint8_t *data, size_t size, uint32_t ip, int encoding
   x86_Convert_Init(st);
   (void)x86_Convert(data, size, ip, &st, encoding);
 }
+size_t refh_bra_convert(int id, uint8_t *data, size_t size, uint32_t ip, int encoding)
+{
+  switch (id)
+  {
+    case 5: return PPC_Convert(data, size, ip, encoding);
+    case 6: return IA64_Convert(data, size, ip, encoding);
+    case 7: return ARM_Convert(data, size, ip, encoding);
+    case 8: return ARMT_Convert(data, size, ip, encoding);
+    case 9: return SPARC_Convert(data, size, ip, encoding);
+  }
+  return 0;
+}
 void refh_delta(uint8_t *data, size_t size, unsigned delta, int encoding)
 {
   Byte st[DELTA_STATE_SIZE];
@@ -566,4 +581,88 @@ size_t refh_sizeof(int which)
     case 3: return sizeof(CLzmaProps);
     default: return 0;
   }
+}
+
+/* ---------------- 7z archive: open + extract every file (7zMain.c pattern, from memory) ---------------- */
+/* the fork's file helpers reference two Win32-only openers (7zFile.h:36-37); never called here */
+int InFile_OpenW(void *p, const void *name, int writeMode) { (void)p; (void)name; (void)writeMode; return 1; }
+int OutFile_OpenW(void *p, const void *name, int writeMode) { (void)p; (void)name; (void)writeMode; return 1; }
+
+typedef struct { ISeekInStream s; const uint8_t *data; size_t size, pos; } MemSeekIn;
+
+static SRes mem_read(void *pp, void *buf, size_t *size)
+{
+  MemSeekIn *m = (MemSeekIn *)pp;
+  size_t n = m->size - m->pos;
+  if (n > *size) n = *size;
+  memcpy(buf, m->data + m->pos, n);
+  m->pos += n;
+  *size = n;
+  return SZ_OK;
+}
+
+static SRes mem_seek(void *pp, Int64 *pos, ESzSeek origin)
+{
+  MemSeekIn *m = (MemSeekIn *)pp;
+  Int64 base = origin == SZ_SEEK_SET ? 0 : (origin == SZ_SEEK_CUR ? (Int64)m->pos : (Int64)m->size);
+  Int64 t = base + *pos;
+  if (t < 0) return SZ_ERROR_FAIL;
+  m->pos = (size_t)t;
+  *pos = t;
+  return SZ_OK;
+}
+
+/* Returns SzArEx_Open's SRes.  For every file i < maxFiles: fileRes = SzArEx_Extract's SRes, fileSize,
+ * fileFolder (0xFFFFFFFF: no stream), fileFlags (bit0 IsDir, bit1 HasStream, bit2 CrcDefined), fileCrc, and
+ * the file's bytes appended to out (fileOff = where).  Names: UTF-16 code units of all names, 0-terminated. */
+int refh_7z_extract_all(const uint8_t *arc, size_t n, uint8_t *out, size_t cap, uint32_t maxFiles,
+                        uint32_t *numFiles, uint32_t *numFolders, int32_t *fileRes, uint64_t *fileOff,
+                        uint64_t *fileSize, uint32_t *fileFolder, uint8_t *fileFlags, uint32_t *fileCrc,
+                        uint16_t *names, size_t namesCap, size_t *namesLen)
+{
+  MemSeekIn mem;
+  CLookToRead look;
+  CSzArEx db;
+  SRes res;
+  size_t op = 0, np = 0;
+  UInt32 i, block = 0xFFFFFFFF;
+  Byte *cache = 0;
+  size_t cacheSize = 0;
+  refh_init();
+  mem.s.Read = mem_read; mem.s.Seek = mem_seek; mem.data = arc; mem.size = n; mem.pos = 0;
+  LookToRead_CreateVTable(&look, False);
+  look.realStream = &mem.s;
+  LookToRead_Init(&look);
+  SzArEx_Init(&db);
+  *numFiles = *numFolders = 0;
+  if (namesLen) *namesLen = 0;
+  res = SzArEx_Open(&db, &look.s, &g_alloc, &g_alloc);
+  if (res != SZ_OK) return res;
+  *numFiles = db.db.NumFiles; *numFolders = db.db.NumFolders;
+  for (i = 0; i < db.db.NumFiles && i < maxFiles; i++)
+  {
+    const CSzFileItem *f = db.db.Files + i;
+    size_t offset = 0, done = 0;
+    SRes r = SzArEx_Extract(&db, &look.s, i, &block, &cache, &cacheSize, &offset, &done, &g_alloc, &g_alloc);
+    fileRes[i] = r;
+    fileSize[i] = f->Size;
+    fileFolder[i] = db.FileIndexToFolderIndexMap[i];
+    fileFlags[i] = (uint8_t)((f->IsDir ? 1 : 0) | (f->HasStream ? 2 : 0) | (f->CrcDefined ? 4 : 0));
+    fileCrc[i] = f->Crc;
+    fileOff[i] = op;
+    if ((r == SZ_OK || r == SZ_ERROR_CRC) && cache && done != 0 && offset + done <= cacheSize && op + done <= cap)
+    {
+      memcpy(out + op, cache + offset, done);
+      op += done;
+    }
+    if (names && db.FileNameOffsets)
+    {
+      size_t len = SzArEx_GetFileNameUtf16(&db, i, NULL);
+      if (np + len <= namesCap) { SzArEx_GetFileNameUtf16(&db, i, names + np); np += len; }
+    }
+  }
+  if (namesLen) *namesLen = np;
+  g_alloc.Free(&g_alloc, cache);
+  SzArEx_Free(&db, &g_alloc);
+  return SZ_OK;
 }

@@ -276,6 +276,13 @@ class _Ref:
         self.L.refh_x86_filter_whole(_ptr(buf), len(buf), ip, encoding)
         return buf
 
+    def bra_convert(self, fid, data, ip=0, encoding=0):
+        buf = as_u8(data).copy()
+        self.L.refh_bra_convert.restype = C.c_size_t
+        self.L.refh_bra_convert.argtypes = [C.c_int, _u8p, C.c_size_t, C.c_uint32, C.c_int]
+        n = self.L.refh_bra_convert(fid, _ptr(buf), len(buf), ip, encoding)
+        return buf, int(n)
+
     def delta(self, data, dist, encoding=0):
         buf = as_u8(data).copy()
         self.L.refh_delta(_ptr(buf), len(buf), dist, encoding)
@@ -470,6 +477,13 @@ class _Oracle:
 
     def x86_filter_whole(self, data, ip=0, encoding=0):
         return self.x86_convert(data, ip, 0, encoding)[0]
+
+    def bra_convert(self, fid, data, ip=0, encoding=0):
+        buf = as_u8(data).copy()
+        self.L.ora_bra_convert.restype = C.c_size_t
+        self.L.ora_bra_convert.argtypes = [C.c_int, _u8p, C.c_size_t, C.c_uint32, C.c_int]
+        n = self.L.ora_bra_convert(fid, _ptr(buf), len(buf), ip, encoding)
+        return buf, int(n)
 
     def delta(self, data, dist, encoding=0):
         buf = as_u8(data).copy()

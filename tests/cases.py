@@ -75,3 +75,27 @@ def check_filter_case(impl, c, blobs):
         seg = data[: c["n"]]
         assert impl.crc32(seg) == c["crc32"], c
         assert impl.crc64(seg) == c["crc64"], c
+
+
+# ---- stateless branch converters + Delta_Encode (tests/golden/bra.json, tools/make_golden_bra.py)
+_bra = None
+
+
+def bra_golden():
+    global _bra
+    if _bra is None:
+        import json
+        j = json.load(open(os.path.join(HERE, "golden", "bra.json")))
+        z = np.load(os.path.join(HERE, "golden", "bra.npz"))
+        _bra = (j["cases"], {k: z[k] for k in z.files})
+    return _bra
+
+
+def check_bra_case(impl, c, blobs):
+    data = blobs[c["blob"]][: c["n"]]
+    if c["kind"] == "bra":
+        out, done = impl.bra_convert(c["id"], data, c["ip"], c["enc"])
+        assert done == c["processed"], (c, done)
+    else:
+        out = impl.delta(data, c["dist"], 1)
+    assert zlib.crc32(np.asarray(out).tobytes()) == c["out_crc"], c

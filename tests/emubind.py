@@ -118,8 +118,13 @@ class Emu:
         return out, int(r["src_used"]), int(r["status"])
 
     def delta(self, data, dist, encoding=0):
-        assert encoding == 0
-        return self._post(data, filter=3, filter_param=dist)[0]
+        return self._post(data, filter=3, filter_param=dist, flags=2 if encoding else 0)[0]
+
+    def bra_convert(self, fid, data, ip=0, encoding=0):
+        if len(data) < (16 if fid == 6 else 4):
+            return np.ascontiguousarray(data, dtype=np.uint8).copy(), 0
+        out, r = self._post(data, filter=fid, filter_param=ip, flags=4 | (2 if encoding else 0))
+        return out, int(r["src_used"])
 
     def crc32(self, data):
         return int(self._post(data, check=1)[1]["check"])

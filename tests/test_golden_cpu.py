@@ -54,6 +54,22 @@ def test_kernel_logic_reproduces_golden_filters(emu, kind):
         cases.check_filter_case(emu, c, blobs)
 
 
+def test_branch_converters_and_delta_encode(ora, emu):
+    """ARM / ARMT / PPC / SPARC / IA64 and Delta_Encode: oracle and kernel logic vs the reference's outputs."""
+    cs, blobs = cases.bra_golden()
+    assert len(cs) > 300
+    for impl in (ora, emu):
+        for c in cs:
+            cases.check_bra_case(impl, c, blobs)
+
+
+@pytest.mark.needref
+def test_branch_converter_golden_equals_live_reference(ref):
+    cs, blobs = cases.bra_golden()
+    for c in cs[::5]:
+        cases.check_bra_case(ref, c, blobs)
+
+
 def test_kernel_logic_fused_filter_and_check(emu, ora):
     """decode -> BCJ -> CRC64 in one pass (what an xz block with one unit asks of a warp)."""
     import lzb200

@@ -33,7 +33,10 @@ class Gpu:
         return lzb200.sdk.x86_convert(data, ip, state, encoding)
 
     def delta(self, data, dist, encoding=0):
-        return lzb200.sdk.delta_decode(data, dist)[0]
+        return (lzb200.sdk.delta_encode if encoding else lzb200.sdk.delta_decode)(data, dist)[0]
+
+    def bra_convert(self, fid, data, ip=0, encoding=0):
+        return lzb200.sdk.bra_convert(fid, data, ip, encoding)
 
     def crc32(self, data):
         return lzb200.sdk.crc32(data)
@@ -94,6 +97,12 @@ def test_golden_filters_and_checks(gpu, kind):
     blobs, _ = cases.golden()
     for c in cases.cases_of(kind):
         cases.check_filter_case(gpu, c, blobs)
+
+
+def test_golden_branch_converters_and_delta_encode(gpu):
+    cs, blobs = cases.bra_golden()
+    for c in cs:
+        cases.check_bra_case(gpu, c, blobs)
 
 
 # ------------------------------------------------------------------ fresh inputs vs the oracle

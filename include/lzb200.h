@@ -360,6 +360,52 @@ SRes XzDecodeParallel(LzbContext *ctx, Byte *dest, SizeT *destLen, const Byte *s
 SRes Xz_ReadIndexBackward(const Byte *src, size_t srcLen, LzbXzBlock *blocks, size_t maxBlocks, size_t *n,
                           int *checkType);
 
+/* ---- 7z folder path (reference 7zIn.c SzArEx_Open / SzArEx_Extract, 7zDec.c SzFolder_Decode) ----
+ * The archive database is parsed on the host (the LZMA-packed header is decoded on the GPU); all folders of
+ * the archive are then decoded in one batched GPU pass, with BCJ x86 / ARM, the folder CRC-32 and every
+ * file's CRC-32 computed on the device. */
+typedef struct LzbSzFolder
+{
+  uint64_t pack_off;        /* absolute offset of the folder's packed stream in the archive            */
+  uint64_t pack_size;
+  uint64_t unpack_size;
+  uint64_t out_off;         /* where SzArchive_ExtractAll puts the folder's bytes in the output arena   */
+  uint32_t method;          /* 0 Copy, 1 LZMA, 2 LZMA2                                                  */
+  uint32_t filter;          /* 0 none, 4 BCJ x86, 7 ARM (xz filter ids)                                 */
+  uint32_t crc;
+  uint8_t crc_defined, props_size;
+  uint8_t supported;        /* SRes of the reference's CheckSupportedFolder (7zDec.c:269-331)           */
+  uint8_t pad_;
+  uint8_t props[8];
+  uint32_t first_file, num_streams;
+} LzbSzFolder;
+
+typedef struct LzbSzFile
+{
+  uint64_t size;
+  uint64_t out_off;         /* offset of the file's bytes in the output arena (files with a stream)     */
+  uint32_t folder;          /* 0xFFFFFFFF: no folder (empty file / directory)                           */
+  uint32_t crc;
+  uint8_t crc_defined, is_dir, has_stream, attrib_defined, mtime_defined, pad_[3];
+  uint32_t name_off, name_len;   /* UTF-16 code units in SzArchive_Names(), name_len includes the 0     */
+  uint32_t attrib, mtime_lo, mtime_hi;
+} LzbSzFile;
+
+typedef struct LzbSzArchive LzbSzArchive;
+/* SzArEx_Open's result codes (7z.h:197-205) for an archive held in memory. */
+SRes SzArchive_Open(LzbContext *ctx, const Byte *archive, size_t size, LzbSzArchive **out);
+void SzArchive_Free(LzbSzArchive *a);
+size_t SzArchive_NumFolders(const LzbSzArchive *a);
+size_t SzArchive_NumFiles(const LzbSzArchive *a);
+const LzbSzFolder *SzArchive_Folders(const LzbSzArchive *a);
+const LzbSzFile *SzArchive_Files(const LzbSzArchive *a);
+const UInt16 *SzArchive_Names(const LzbSzArchive *a, size_t *numUnits);
+UInt64 SzArchive_UnpackSize(const LzbSzArchive *a);
+/* Decode every folder into out[0 .. SzArchive_UnpackSize).  folderRes[i]: SzFolder_Decode + folder CRC verdict;
+ * fileRes[k]: what SzArEx_Extract returns for file k (7zIn.c:1322-1405).  Either may be NULL. */
+SRes SzArchive_ExtractAll(LzbContext *ctx, const LzbSzArchive *a, const Byte *archive, size_t size, Byte *out, size_t outCap,
+                          SRes *folderRes, SRes *fileRes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "liblzb200.so")
-SOURCES = ["lzb_kernels.cu", "lzb_host.cu", "lzb_containers.cu", "lzb_state.cu", "lzb_xzstream.cu"]
+SOURCES = ["lzb_kernels.cu", "lzb_host.cu", "lzb_containers.cu", "lzb_state.cu", "lzb_xzstream.cu", "lzb_7z.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--use_fast_math"]
 

@@ -328,6 +328,49 @@ SRes lzb_run_resident(LzbContext *c, const uint8_t *d_packed, uint8_t *d_out, co
   return SZ_OK;
 }
 
+/* One archive, several dependent passes over the same device-resident arenas (7z folder path): upload the
+ * packed bytes once, device-to-device copies for stored ranges, the fused decode pass, then up to two
+ * filter/check-only passes (folder level, then file level), one download of the output at the end. */
+SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+                    const LzbCopyRange *copies, size_t n_copies,
+                    const LzbUnit *units, LzbResult *results, size_t n,
+                    const LzbUnit *post_a, LzbResult *res_a, size_t n_a,
+                    const LzbUnit *post_b, LzbResult *res_b, size_t n_b)
+{
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
+  LzbSlot &s = c->slot[0];
+  const ModelBytes model = model_bytes_for(units, n);
+  const size_t most = std::max(n, std::max(n_a, n_b));
+  if (!lzb_slot_reserve(c, s, packedBytes + 16, outBytes + 16, most ? most : 1, n ? slab_bytes_for(model) : 0)) return SZ_ERROR_MEM;
+  bool ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_packed, packed, packedBytes, cudaMemcpyHostToDevice, s.stream), "H2D archive");
+  for (size_t i = 0; ok && i < n_copies; i++)
+    ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_out + copies[i].dst_off, s.d_packed + copies[i].src_off, copies[i].len,
+                                     cudaMemcpyDeviceToDevice, s.stream), "stored folder copy");
+  if (!ok) return SZ_ERROR_FAIL;
+  if (n)
+  {
+    if (!lzb_cuda_ok(cudaMemcpyAsync(s.d_units, units, n * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D units")) return SZ_ERROR_FAIL;
+    int rc = lzb_launch_decode(s.d_packed, s.d_out, s.d_units, s.d_results, (uint32_t)n, s.d_ticket, model.smem, model.gmem, s.d_slab, s.stream);
+    if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+    if (!lzb_cuda_ok(cudaMemcpyAsync(results, s.d_results, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results")) return SZ_ERROR_FAIL;
+  }
+  const LzbUnit *pu[2] = { post_a, post_b };
+  LzbResult *pr[2] = { res_a, res_b };
+  const size_t pn[2] = { n_a, n_b };
+  for (int k = 0; k < 2; k++)
+  {
+    if (!pn[k]) continue;
+    if (!lzb_cuda_ok(cudaMemcpyAsync(s.d_units, pu[k], pn[k] * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D post units")) return SZ_ERROR_FAIL;
+    int rc = lzb_launch_post_only(s.d_out, s.d_units, s.d_results, (uint32_t)pn[k], s.stream);
+    if (rc != 0) { lzb_set_error("post launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+    if (!lzb_cuda_ok(cudaMemcpyAsync(pr[k], s.d_results, pn[k] * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H post results")) return SZ_ERROR_FAIL;
+  }
+  if (outBytes && !lzb_cuda_ok(cudaMemcpyAsync(out, s.d_out, outBytes, cudaMemcpyDeviceToHost, s.stream), "D2H output")) return SZ_ERROR_FAIL;
+  if (!lzb_cuda_ok(cudaStreamSynchronize(s.stream), "7z passes")) return SZ_ERROR_FAIL;
+  return SZ_OK;
+}
+
 SRes lzb_decode_host_simple(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
                             const LzbUnit *units, LzbResult *results, size_t n)
 {

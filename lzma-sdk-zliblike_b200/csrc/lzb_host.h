@@ -46,6 +46,13 @@ bool lzb_slot_reserve(LzbContext *c, LzbSlot &s, size_t packed, size_t out, size
 SRes lzb_decode_host_simple(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
                             const LzbUnit *units, LzbResult *results, size_t n);
 
+struct LzbCopyRange { uint64_t src_off, dst_off, len; };
+SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+                    const LzbCopyRange *copies, size_t n_copies,
+                    const LzbUnit *units, LzbResult *results, size_t n,
+                    const LzbUnit *post_a, LzbResult *res_a, size_t n_a,
+                    const LzbUnit *post_b, LzbResult *res_b, size_t n_b);
+
 SRes lzb_run_resident(LzbContext *c, const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *units, LzbResult *results, size_t n);
 
 /* little helpers */

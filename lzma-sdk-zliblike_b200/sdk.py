@@ -218,3 +218,65 @@ def raw_lzma_units(src_offs, src_lens, dst_offs, dst_caps, props, finish: int = 
     u["src_off"], u["src_len"], u["dst_off"], u["dst_cap"] = src_offs, src_lens, dst_offs, dst_caps
     u["dict_size"], u["codec"], u["lc"], u["lp"], u["pb"], u["finish"] = ds, R.CODEC_LZMA, lc, lp, pb, finish
     return u
+
+
+# ----------------------------------------------------------------------------- 7z folder path
+SZ_FOLDER_DTYPE = np.dtype([("pack_off", "<u8"), ("pack_size", "<u8"), ("unpack_size", "<u8"), ("out_off", "<u8"),
+                            ("method", "<u4"), ("filter", "<u4"), ("crc", "<u4"), ("crc_defined", "u1"), ("props_size", "u1"),
+                            ("supported", "u1"), ("pad_", "u1"), ("props", "u1", (8,)), ("first_file", "<u4"),
+                            ("num_streams", "<u4")])
+SZ_FILE_DTYPE = np.dtype([("size", "<u8"), ("out_off", "<u8"), ("folder", "<u4"), ("crc", "<u4"), ("crc_defined", "u1"),
+                          ("is_dir", "u1"), ("has_stream", "u1"), ("attrib_defined", "u1"), ("mtime_defined", "u1"),
+                          ("pad_", "u1", (3,)), ("name_off", "<u4"), ("name_len", "<u4"), ("attrib", "<u4"),
+                          ("mtime_lo", "<u4"), ("mtime_hi", "<u4"), ("pad2_", "<u4")])
+assert SZ_FOLDER_DTYPE.itemsize == 64 and SZ_FILE_DTYPE.itemsize == 56
+
+
+def sz_extract_all(archive, ctx=None) -> dict:
+    """SzArchive_Open + SzArchive_ExtractAll: the reference's SzArEx_Open / SzArEx_Extract for every file."""
+    L = _lib.load()
+    arc = _u8(archive)
+    L.SzArchive_Open.restype = C.c_int
+    L.SzArchive_Open.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.SzArchive_Free.argtypes = [C.c_void_p]
+    for f in ("SzArchive_NumFolders", "SzArchive_NumFiles"):
+        getattr(L, f).restype = C.c_size_t
+        getattr(L, f).argtypes = [C.c_void_p]
+    for f in ("SzArchive_Folders", "SzArchive_Files"):
+        getattr(L, f).restype = C.c_void_p
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.SzArchive_Names.restype = C.c_void_p
+    L.SzArchive_Names.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+    L.SzArchive_UnpackSize.restype = C.c_uint64
+    L.SzArchive_UnpackSize.argtypes = [C.c_void_p]
+    L.SzArchive_ExtractAll.restype = C.c_int
+    L.SzArchive_ExtractAll.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    h = C.c_void_p(None)
+    r = L.SzArchive_Open(ctx.h if ctx else None, _p(arc), len(arc), C.byref(h))
+    if r == R.SZ_ERROR_FAIL:
+        raise _lib.LzbError(_lib.last_error())
+    if r != 0:
+        return dict(open_res=r, num_files=0, num_folders=0, files=[], folder_res=[], out=np.zeros(0, np.uint8))
+    try:
+        nfo, nfi = L.SzArchive_NumFolders(h), L.SzArchive_NumFiles(h)
+        folders = np.ctypeslib.as_array(C.cast(L.SzArchive_Folders(h), C.POINTER(C.c_uint8)), shape=(max(nfo, 1) * 64,))[: nfo * 64].view(SZ_FOLDER_DTYPE).copy() if nfo else np.zeros(0, SZ_FOLDER_DTYPE)
+        files = np.ctypeslib.as_array(C.cast(L.SzArchive_Files(h), C.POINTER(C.c_uint8)), shape=(max(nfi, 1) * 56,))[: nfi * 56].view(SZ_FILE_DTYPE).copy() if nfi else np.zeros(0, SZ_FILE_DTYPE)
+        nn = C.c_size_t(0)
+        pn = L.SzArchive_Names(h, C.byref(nn))
+        names = np.ctypeslib.as_array(C.cast(pn, C.POINTER(C.c_uint16)), shape=(nn.value,)).copy() if nn.value else np.zeros(0, np.uint16)
+        total = int(L.SzArchive_UnpackSize(h))
+        out = np.zeros(total + 16, np.uint8)
+        fres, ires = np.zeros(max(nfo, 1), np.int32), np.zeros(max(nfi, 1), np.int32)
+        r2 = L.SzArchive_ExtractAll(ctx.h if ctx else None, h, _p(arc), len(arc), _p(out), total, _p(fres), _p(ires))
+        if r2 == R.SZ_ERROR_FAIL:
+            raise _lib.LzbError(_lib.last_error())
+        flist = []
+        for k in range(nfi):
+            f = files[k]
+            nm = names[int(f["name_off"]): int(f["name_off"]) + max(int(f["name_len"]) - 1, 0)].tobytes().decode("utf-16-le") if len(names) else None
+            flist.append(dict(res=int(ires[k]), off=int(f["out_off"]), size=int(f["size"]), folder=int(f["folder"]), is_dir=bool(f["is_dir"]),
+                              has_stream=bool(f["has_stream"]), crc_defined=bool(f["crc_defined"]), crc=int(f["crc"]), name=nm))
+        return dict(open_res=0, extract_res=r2, num_files=nfi, num_folders=nfo, files=flist, folder_res=[int(x) for x in fres[:nfo]],
+                    folders=folders, out=out[:total])
+    finally:
+        L.SzArchive_Free(h)

@@ -655,6 +655,14 @@ int refh_7z_extract_all(const uint8_t *arc, size_t n, uint8_t *out, size_t cap, 
       memcpy(out + op, cache + offset, done);
       op += done;
     }
+    if (r != SZ_OK)
+    {
+      /* 7zMain stops at the first failure; to get a verdict for EVERY file the solid-block cache is dropped
+       * after a failure, so that the next file of the same folder decodes it again instead of reading the
+       * half-written cache (7zIn.c:1345) */
+      g_alloc.Free(&g_alloc, cache);
+      cache = 0; cacheSize = 0; block = 0xFFFFFFFF;
+    }
     if (names && db.FileNameOffsets)
     {
       size_t len = SzArEx_GetFileNameUtf16(&db, i, NULL);

@@ -264,6 +264,30 @@ class _Ref:
                                               _ptr(done, _u32p), threads, 1 if scratch else 0)
         return dict(secs=secs, res=res, dst_done=done, out=dst)
 
+    # ---- 7z archive: SzArEx_Open + SzArEx_Extract for every file ----
+    def sz_extract_all(self, archive, out_cap=None, max_files=4096):
+        arc = as_u8(archive)
+        cap = out_cap if out_cap is not None else max(len(arc) * 40, 1 << 20)
+        out = np.zeros(cap, dtype=np.uint8)
+        nf, nfo = C.c_uint32(0), C.c_uint32(0)
+        res = np.zeros(max_files, np.int32); off = np.zeros(max_files, np.uint64); size = np.zeros(max_files, np.uint64)
+        folder = np.zeros(max_files, np.uint32); flags = np.zeros(max_files, np.uint8); crc = np.zeros(max_files, np.uint32)
+        names = np.zeros(1 << 16, np.uint16)
+        nl = C.c_size_t(0)
+        f = self.L.refh_7z_extract_all
+        f.restype = C.c_int
+        f.argtypes = [_u8p, C.c_size_t, _u8p, C.c_size_t, C.c_uint32, _u32p, _u32p, _i32p, _u64p, _u64p, _u32p, _u8p,
+                      _u32p, C.POINTER(C.c_uint16), C.c_size_t, _szp]
+        r = f(_ptr(arc), len(arc), _ptr(out), cap, max_files, C.byref(nf), C.byref(nfo), _ptr(res, _i32p), _ptr(off, _u64p),
+              _ptr(size, _u64p), _ptr(folder, _u32p), _ptr(flags), _ptr(crc, _u32p),
+              names.ctypes.data_as(C.POINTER(C.c_uint16)), len(names), C.byref(nl))
+        n = min(nf.value, max_files)
+        text = names[: nl.value].tobytes().decode("utf-16-le").split("\0")[:n] if nl.value else []
+        files = [dict(res=int(res[i]), off=int(off[i]), size=int(size[i]), folder=int(folder[i]), is_dir=bool(flags[i] & 1),
+                      has_stream=bool(flags[i] & 2), crc_defined=bool(flags[i] & 4), crc=int(crc[i]),
+                      name=text[i] if i < len(text) else None) for i in range(n)]
+        return dict(open_res=int(r), num_files=nf.value, num_folders=nfo.value, files=files, out=out)
+
     # ---- filters / checks ----
     def x86_convert(self, data, ip=0, state=0, encoding=0):
         buf = as_u8(data).copy()

@@ -1,0 +1,94 @@
+"""The 7z folder path (BASELINE config 5): SzArchive_Open / SzArchive_ExtractAll must answer
+what the reference's SzArEx_Open and SzArEx_Extract answer -- for the database (file table, names, folder
+map), for every file's bytes, and for the result codes of damaged archives.
+
+Golden: tests/golden/sz.json (tools/make_golden_7z.py): archives written by tools/sz_writer.py from payloads
+the reference's encoders made (Copy / LZMA / LZMA2, BCJ x86, ARM, Delta-as-unsupported, packed header, many
+small folders from low entropy to random, empty files and directories), pristine and with 29 mutations each.
+
+CPU part : vectors vs the live reference (needref); the writer's own listing; the public structs.
+GPU part : liblzb200.so vs the vectors.
+"""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from tools.make_golden_7z import mutate, summarize
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def golden():
+    j = json.load(open(os.path.join(HERE, "golden", "sz.json")))
+    z = np.load(os.path.join(HERE, "golden", "sz.npz"))
+    return j["cases"], {k: z[k].tobytes() for k in z.files}
+
+
+def compare(got, want, tag):
+    assert got["open_res"] == want["open_res"], (tag, got["open_res"], want["open_res"])
+    if want["open_res"] != 0:
+        return
+    assert (got["num_files"], got["num_folders"]) == (want["num_files"], want["num_folders"]), tag
+    for k, (a, b) in enumerate(zip(got["files"], want["files"])):
+        assert a == b, (tag, k, a, b)
+
+
+@pytest.mark.needref
+def test_golden_equals_live_reference(ref):
+    cases, blobs = golden()
+    for c in cases[::4]:
+        m = tuple(c["mut"]) if c["mut"] else None
+        compare(summarize(ref.sz_extract_all(mutate(blobs[c["blob"]], m))), c, (c["blob"], c["mut"]))
+
+
+def test_golden_is_meaningful():
+    cases, blobs = golden()
+    assert len(cases) >= 150
+    assert {c["open_res"] for c in cases} >= {0, 3, 4, 6, 16, 17}
+    assert {f["res"] for c in cases for f in c["files"]} >= {0, 1, 3, 4}
+    whole = [c for c in cases if c["mut"] is None]
+    assert len(whole) == 5 and sum(c["num_folders"] for c in whole) > 70
+    assert any(f["is_dir"] for c in whole for f in c["files"]) and any(not f["has_stream"] and not f["is_dir"] for c in whole for f in c["files"])
+
+
+def test_public_structs_have_the_documented_size():
+    import lzb200
+    assert lzb200.sdk.SZ_FOLDER_DTYPE.itemsize == 64 and lzb200.sdk.SZ_FILE_DTYPE.itemsize == 56
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("blob", ["a_plain", "a_packed_header", "b_many", "c_delta_unsupported", "d_empty_only"])
+def test_product_matches_golden(blob):
+    import lzb200
+    cases, blobs = golden()
+    mine = [c for c in cases if c["blob"] == blob]
+    assert mine
+    for c in mine:
+        m = tuple(c["mut"]) if c["mut"] else None
+        d = lzb200.sdk.sz_extract_all(mutate(blobs[blob], m))
+        compare(summarize(d), c, (blob, c["mut"]))
+
+
+@pytest.mark.gpu
+def test_all_folders_in_one_pass_and_bytes_match_the_writer():
+    """fresh archive (not in the golden set): 200 folders, every byte compared with what was stored"""
+    import lzb200
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("needs the reference encoder to write a fresh archive")
+    from tools import sz_writer as W
+    ref = refbind.ref()
+    rng = np.random.default_rng(1)
+    folders = []
+    for i in range(200):
+        n = int(rng.integers(100, 20000))
+        data = np.where(rng.random(n) < i / 199.0, rng.integers(0, 256, n), (np.arange(n) // 5) % 11).astype(np.uint8).tobytes()
+        folders.append(W.Folder("lzma2" if i & 1 else "lzma", [(f"n{i}.bin", data)], filt="bcj" if i % 7 == 0 else None, dict_size=1 << 15))
+    arc = W.write_archive(ref, folders, encode_header=True)
+    d = lzb200.sdk.sz_extract_all(arc)
+    assert d["open_res"] == 0 and d["num_folders"] == 200 and all(r == 0 for r in d["folder_res"])
+    for f, (nm, data) in zip(d["files"], W.expected_listing(folders)):
+        assert f["res"] == 0 and f["name"] == nm and d["out"][f["off"]:f["off"] + f["size"]].tobytes() == data

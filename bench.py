@@ -205,10 +205,25 @@ def cpu_reference_run(w, t, name: str, threads: int, sample_units: int, repeat: 
     sub = dict(t)
     sub["idx"] = t["idx"][:n]
     fill_packed(packed, w, sub)
+    if kind == 2:
+        # xz leg: each block wrapped as a one-block .xz member so the whole XzUnpacker path (block header,
+        # LZMA2, BCJ, CRC-64, index, footer) is timed, one member per host thread
+        uniq = len(w["plen"])
+        ustart = np.concatenate(([0], np.cumsum(w["plen"].astype(np.uint64))[:-1]))
+        members = [ref.xz_assemble(w["blob"][int(ustart[k]):int(ustart[k]) + int(w["plen"][k])], [0], [int(w["plen"][k])],
+                                   [int(w["ulen"][k])], [int(w["crc64"][k])], 4, 4, 0, int(w["props"][0])) for k in range(uniq)]
+        idx = t["idx"][:n]
+        mlen = np.array([len(members[int(k)]) for k in idx], dtype=np.uint32)
+        moff = np.concatenate(([0], np.cumsum((mlen.astype(np.uint64) + 15) & ~np.uint64(15))[:-1])).astype(np.uint64)
+        arena = np.zeros(int(moff[-1]) + int(mlen[-1]) + 64, dtype=np.uint8)
+        for i, k in enumerate(idx):
+            arena[int(moff[i]):int(moff[i]) + int(mlen[i])] = members[int(k)]
+        for _ in range(repeat):
+            r = ref.xz_decode_batch_mt(arena, moff, mlen, t["doff"][:n], t["ulen"][:n].astype(np.uint32), threads, scratch=True)
+            assert (r["res"] == 0).all() and (r["dst_done"] == t["ulen"][:n]).all(), "reference xz decode failed"
+            best = r["secs"] if best is None else min(best, r["secs"])
+        return dict(secs=best, out_bytes=int(t["ulen"][:n].sum()), units=n)
     for _ in range(repeat):
-        if kind == 2:
-            # xz leg: each unit wrapped as a one-block .xz member so the whole XzUnpacker path is timed
-            raise NotImplementedError
         r = ref.decode_batch_mt(0 if kind == 0 else 1, packed, t["soff"][:n], t["plen"][:n].astype(np.uint32),
                                 t["doff"][:n], t["ulen"][:n].astype(np.uint32), w["props"],
                                 0 if kind == 0 else 1, threads, scratch=True)
@@ -249,8 +264,6 @@ def main():
             return 0
         w = build_workload(a.workload, 0, cache, a.small)
         t = tile_units(w, n_units, a.workload)
-        if int(w["kind"]) == 2:
-            w = dict(w); w["kind"] = 1   # timed as the LZMA2 unit decode (dominant cost of the xz block path)
         sample = min(n_units, max(64, (512 if a.workload == "lzma64k" else 8) * threads))
         for _ in range(max(a.warmup, 0) and 1):
             cpu_reference_run(w, t, a.workload, threads, min(sample, 4 * threads))
@@ -262,7 +275,7 @@ def main():
                     data="synthetic", config=cfg, impl="reference",
                     cpu_baseline=dict(value=v, unit="GB/s", cores=threads, kind="reference",
                                       sample=f"{times[0]['units']} units ({times[0]['out_bytes'] / 2**20:.0f} MiB out) per step, "
-                                             f"one unit per thread, unmodified LzmaDec/Lzma2Dec (oracle/_ref/libref.so)"),
+                                             f"one unit per thread, unmodified LzmaDec/Lzma2Dec/XzUnpacker (oracle/_ref/libref.so)"),
                     e2e=dict(value=v, unit="GB/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return 0
@@ -400,8 +413,6 @@ def main():
         from oracle import refbind
         if refbind.have_ref():
             wc = dict(w)
-            if int(w["kind"]) == 2:
-                wc["kind"] = 1
             sample = min(n_units, max(64, (512 if a.workload == "lzma64k" else 8) * threads))
             cpu_reference_run(wc, t, a.workload, threads, min(sample, 4 * threads))
             r = cpu_reference_run(wc, t, a.workload, threads, sample)

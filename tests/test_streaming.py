@@ -116,3 +116,19 @@ def test_gpu_lzma2_whole_buffer_goes_parallel_and_matches(ora):
     assert (r, st.value, d.decoder.dicPos, sl.value) == (want["res"], want["status"], want["dest_len"], want["src_len"])
     assert np.array_equal(out, want["out"])
     L.LzmaDec_FreeProbs(C.byref(d.decoder), C.byref(_alloc))
+
+
+@pytest.mark.gpu
+@pytest.mark.needref
+def test_gpu_config1_shape_single_stream_with_ring_dictionary(ref):
+    """BASELINE config 1 in small: one long stream through LzmaDec_DecodeToBuf (the LzmaUtil loop), dictionary
+    much smaller than the stream so the ring wraps many times; fed 64 KiB in / 64 KiB out like LzmaUtil.c:55-106."""
+    from tools.corpus import make_corpus
+    plain = make_corpus(3 << 20, seed=41)
+    packed, props = ref.lzma_encode(plain, level=1, dict_size=1 << 18, end_mark=1)
+    g = GpuStream()
+    for ic, oc in ((1 << 16, 1 << 16), (100000, 1 << 20)):
+        a = ref.lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
+        b = g.lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
+        same(a, b)
+        assert np.array_equal(b["out"][: len(plain)], plain)

@@ -13,6 +13,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 
 /* ------------------------------------------------------------------ errors ----------------- */
 static thread_local char g_err[512] = "";
@@ -75,6 +77,10 @@ extern "C" void Lzb_Destroy(LzbContext *c)
     if (s.h_results) cudaFreeHost(s.h_results);
   }
   cudaFree(c->d_dev_tickets); cudaFree(c->d_dev_slab);
+  cudaFree(c->d_flow);
+  if (c->h_flow) cudaFreeHost(c->h_flow);
+  if (c->h_one) cudaFreeHost(c->h_one);
+  if (c->flow_event) cudaEventDestroy(c->flow_event);
   delete c;
 }
 
@@ -224,19 +230,164 @@ static void make_slices(const LzbUnit *u, size_t n, size_t min_units, std::vecto
   }
 }
 
+/* ------------------------------------------------------------------ streamed launch ---------- */
+/* ONE persistent launch for the whole batch, fed and drained while it runs: the packed arena goes up in chunks
+ * on a copy stream (each chunk followed by its arrival flag), the kernel takes units in index order and waits
+ * for a unit's chunk, and the group that completes a chunk raises a flag in mapped host memory, on which this
+ * thread starts the chunk's download on a third stream.  Compared with sliced launches there is no per-slice
+ * drain (a unit takes tens of milliseconds) and the copies of the first and last slice are not exposed. */
+static const uint64_t kFlowChunkBytes = 32ull << 20;
+static const size_t kFlowMaxChunks = 8192;
+
+static bool flow_reserve(LzbContext *c, size_t n_chunks)
+{
+  if (!c->h_one)
+  {
+    if (!lzb_cuda_ok(cudaHostAlloc((void **)&c->h_one, 64, cudaHostAllocDefault), "cudaHostAlloc flow constant")) return false;
+    c->h_one[0] = 1;
+  }
+  if (!c->flow_event && !lzb_cuda_ok(cudaEventCreateWithFlags(&c->flow_event, cudaEventDisableTiming), "cudaEventCreate")) return false;
+  if (n_chunks + 16 <= c->flow_cap) return true;
+  cudaFree(c->d_flow); c->d_flow = nullptr;
+  if (c->h_flow) { cudaFreeHost(c->h_flow); c->h_flow = nullptr; }
+  c->flow_cap = 0;
+  const size_t want = n_chunks + n_chunks / 4 + 64;
+  if (!lzb_cuda_ok(cudaMalloc((void **)&c->d_flow, 2 * want * sizeof(uint32_t)), "cudaMalloc flow flags")) return false;
+  if (!lzb_cuda_ok(cudaHostAlloc((void **)&c->h_flow, (want + 16) * sizeof(uint32_t), cudaHostAllocMapped), "cudaHostAlloc flow flags")) return false;
+  if (!lzb_cuda_ok(cudaHostGetDevicePointer((void **)&c->h_flow_dev, c->h_flow, 0), "cudaHostGetDevicePointer")) return false;
+  c->flow_cap = want;
+  return true;
+}
+
+/* units in index order must walk both arenas forwards without overlap (what every front end here produces) */
+static bool flow_layout_ok(const LzbUnit *u, size_t n)
+{
+  for (size_t i = 1; i < n; i++)
+    if (u[i].src_off < u[i - 1].src_off + u[i - 1].src_len || u[i].dst_off < u[i - 1].dst_off + u[i - 1].dst_cap) return false;
+  return true;
+}
+
+static SRes decode_units_flow(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+                              const LzbUnit *units, LzbResult *results, size_t n, const ModelBytes &model, size_t slab,
+                              uint64_t total_out)
+{
+  size_t chunk_units = (size_t)std::max<uint64_t>(1, (uint64_t)n * kFlowChunkBytes / std::max<uint64_t>(total_out, 1));
+  if (chunk_units > n) chunk_units = n;
+  while ((n + chunk_units - 1) / chunk_units > kFlowMaxChunks) chunk_units *= 2;
+  const size_t n_chunks = (n + chunk_units - 1) / chunk_units;
+  LzbSlot &s = c->slot[0];
+  cudaStream_t s_run = c->slot[0].stream, s_up = c->slot[1].stream, s_down = c->slot[2].stream;
+  if (!lzb_slot_reserve(c, s, packedBytes, outBytes, n, slab) || !flow_reserve(c, n_chunks)) return SZ_ERROR_MEM;
+  uint32_t *d_arrived = c->d_flow, *d_done = c->d_flow + c->flow_cap;
+  volatile uint32_t *h_ready = c->h_flow;
+  volatile uint32_t *h_abort = c->h_flow + c->flow_cap;
+  for (size_t k = 0; k < n_chunks; k++) h_ready[k] = 0;
+  *h_abort = 0;
+  LzbFlow flow;
+  flow.arrived = d_arrived; flow.done = d_done; flow.ready = c->h_flow_dev; flow.abort = c->h_flow_dev + c->flow_cap;
+  flow.chunk_units = (uint32_t)chunk_units; flow.n_chunks = (uint32_t)n_chunks;
+
+  bool ok = lzb_cuda_ok(cudaMemsetAsync(c->d_flow, 0, 2 * c->flow_cap * sizeof(uint32_t), s_run), "flow flags") &&
+            lzb_cuda_ok(cudaEventRecord(c->flow_event, s_run), "flow event") &&
+            lzb_cuda_ok(cudaStreamWaitEvent(s_up, c->flow_event, 0), "flow wait") &&
+            lzb_cuda_ok(cudaMemcpyAsync(s.d_units, units, n * sizeof(LzbUnit), cudaMemcpyHostToDevice, s_run), "H2D units");
+  if (!ok) return SZ_ERROR_FAIL;
+  int rc = lzb_launch_decode_flow(s.d_packed, s.d_out, s.d_units, s.d_results, (uint32_t)n, s.d_ticket, model.smem, model.gmem,
+                                  s.d_slab, &flow, s_run);
+  if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+  /* feed: chunk k's packed bytes, then its flag (stream order = arrival order) */
+  for (size_t k = 0; k < n_chunks && ok; k++)
+  {
+    const size_t a = k * chunk_units, b = std::min(n, a + chunk_units);
+    const uint64_t lo = units[a].src_off, hi = units[b - 1].src_off + units[b - 1].src_len;
+    if (hi > lo) ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_packed + lo, packed + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s_up), "H2D packed chunk");
+    ok = ok && lzb_cuda_ok(cudaMemcpyAsync(d_arrived + k, c->h_one, sizeof(uint32_t), cudaMemcpyHostToDevice, s_up), "H2D arrival flag");
+  }
+  /* drain: as chunks complete */
+  const bool trace = getenv("LZB_FLOW_TRACE") != nullptr;
+  const auto t_start = std::chrono::steady_clock::now();
+  auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+  if (trace) fprintf(stderr, "[flow] %zu units, %zu chunks of %zu units; fed at %.2f ms\n", n, n_chunks, chunk_units, ms_since());
+  SRes ret = ok ? SZ_OK : SZ_ERROR_FAIL;
+  if (!ok) *h_abort = 1;
+  bool up_logged = false;
+  if (trace) cudaEventRecord(c->flow_event, s_up);
+  for (size_t k = 0; k < n_chunks && ret == SZ_OK; k++)
+  {
+    unsigned idle = 0;
+    while (h_ready[k] == 0)
+    {
+      if (trace && !up_logged && cudaEventQuery(c->flow_event) == cudaSuccess) { up_logged = true; fprintf(stderr, "[flow] uploads complete at %.2f ms\n", ms_since()); }
+      if ((++idle & 1023u) == 0)
+      {
+        /* the kernel ending (or failing) without the flag means something went wrong on the device */
+        const cudaError_t q = cudaStreamQuery(s_run);
+        if (q != cudaErrorNotReady && h_ready[k] == 0)
+        {
+          if (q != cudaSuccess) lzb_cuda_ok(q, "streamed decode launch"); else lzb_set_error("streamed launch ended before chunk %zu was complete", k);
+          ret = SZ_ERROR_FAIL;
+          break;
+        }
+      }
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+    if (ret != SZ_OK) break;
+    if (trace && (k % 16 == 0 || k + 1 == n_chunks)) fprintf(stderr, "[flow] chunk %zu ready at %.2f ms\n", k, ms_since());
+    const size_t a = k * chunk_units, b = std::min(n, a + chunk_units);
+    size_t j = a;
+    while (j < b && ok)
+    {
+      uint64_t lo = units[j].dst_off, hi = lo + units[j].dst_cap;
+      size_t e = j + 1;
+      while (e < b && units[e].dst_off == hi) { hi += units[e].dst_cap; e++; }
+      if (hi > lo) ok = lzb_cuda_ok(cudaMemcpyAsync(out + lo, s.d_out + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, s_down), "D2H output chunk");
+      j = e;
+    }
+    if (!ok) ret = SZ_ERROR_FAIL;
+  }
+  if (ret != SZ_OK) *h_abort = 1;
+  ok = lzb_cuda_ok(cudaMemcpyAsync(s.h_results, s.d_results, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s_run), "D2H results");
+  ok = lzb_cuda_ok(cudaStreamSynchronize(s_up), "upload stream") && ok;
+  if (trace) fprintf(stderr, "[flow] upload stream idle at %.2f ms\n", ms_since());
+  ok = lzb_cuda_ok(cudaStreamSynchronize(s_run), "streamed decode launch") && ok;
+  if (trace) fprintf(stderr, "[flow] kernel done at %.2f ms\n", ms_since());
+  ok = lzb_cuda_ok(cudaStreamSynchronize(s_down), "download stream") && ok;
+  if (trace) fprintf(stderr, "[flow] download stream idle at %.2f ms\n", ms_since());
+  if (!ok) return SZ_ERROR_FAIL;
+  memcpy(results, s.h_results, n * sizeof(LzbResult));
+  return ret;
+}
+
 extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
                                     const LzbUnit *units, LzbResult *results, size_t n)
 {
   if (!c) { lzb_set_error("null context"); return SZ_ERROR_PARAM; }
   if (n == 0) return SZ_OK;
+  uint64_t total_out = 0;
   for (size_t i = 0; i < n; i++)
+  {
     if (units[i].src_off + units[i].src_len > packedBytes || units[i].dst_off + units[i].dst_cap > outBytes)
     { lzb_set_error("unit %zu exceeds its arena", i); return SZ_ERROR_PARAM; }
+    total_out += units[i].dst_cap;
+  }
   std::lock_guard<std::mutex> g(c->mu);
   if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
 
   const ModelBytes model = model_bytes_for(units, n);
   const size_t slab = slab_bytes_for(model);
+  /* big batches whose arenas fit in device memory next to each other: one streamed launch */
+  {
+    size_t free_b = 0, total_b = 0;
+    const char *mode = getenv("LZB_FLOW");
+    const bool want = mode ? atoi(mode) != 0 : total_out >= (256ull << 20);
+    if (want && n < 0xFFFFFFFFull && flow_layout_ok(units, n) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+    {
+      const LzbSlot &s0 = c->slot[0];
+      const uint64_t have = (uint64_t)free_b + s0.packed_cap + s0.out_cap;
+      if ((uint64_t)packedBytes + outBytes + (1ull << 30) < have)
+        return decode_units_flow(c, packed, packedBytes, out, outBytes, units, results, n, model, slab, total_out);
+    }
+  }
   std::vector<Slice> slices;
   {
     LzbGeometry geo;

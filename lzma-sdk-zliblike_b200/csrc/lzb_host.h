@@ -34,6 +34,10 @@ struct LzbContext
   uint32_t *d_dev_tickets = nullptr;
   unsigned dev_seq = 0;
   uint8_t *d_dev_slab = nullptr; size_t dev_slab_cap = 0;
+  /* streamed launch (LzbFlow): device flags/counters, mapped host flags, a pinned constant, an event */
+  uint32_t *d_flow = nullptr; uint32_t *h_flow = nullptr; uint32_t *h_flow_dev = nullptr; size_t flow_cap = 0;
+  uint32_t *h_one = nullptr;
+  cudaEvent_t flow_event = nullptr;
   std::mutex mu;
 };
 

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "lzb_core.cuh"
 #include "lzb_post.cuh"
@@ -29,11 +30,65 @@ namespace lzb {
  * budget but a slower schedule: 7.17 vs 7.68 GB/s), G <= 8: 8 warps */
 constexpr uint32_t max_warps_for(uint32_t G) { return G == 32 ? 16u : (G == 16 ? 18u : 8u); }
 
-template <bool kSharedModel, uint32_t G>
+/* ---- a launch that is fed and drained while it runs (LzbFlow, lzb_kernels.h) ---- */
+constexpr long long kFlowTimeoutCycles = 20000000000ll;        /* ~10 s at 2 GHz */
+
+/* wait until unit i's packed bytes (and the chunk after them: a 32-byte sector may straddle the boundary, and
+ * L1 must never see a sector before all of it has landed) are in device memory; false = give up */
+template <uint32_t G> __device__ __noinline__ bool flow_wait(const LzbFlow &f, uint32_t i)
+{
+  typedef Group<G> Grp;
+  const uint32_t c = i / f.chunk_units;
+  const uint32_t need = c + 1 < f.n_chunks ? c + 1 : f.n_chunks - 1;
+  uint32_t ok = 1;
+  if (Grp::lane() == 0)
+  {
+    const long long t0 = clock64();
+    uint32_t v, spins = 0;
+    for (;;)
+    {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.arrived + need) : "memory");
+      if (v != 0) break;
+      __nanosleep(1000);
+      /* the abort word lives in host memory: every group of the GPU polling it over PCIe would starve the
+       * very upload it is waiting for (measured: 0.8 GB/s), so it is looked at every ~16 ms only */
+      if ((++spins & 16383u) == 0)
+      {
+        uint32_t a;
+        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(a) : "l"(f.abort) : "memory");
+        if (a != 0 || clock64() - t0 > kFlowTimeoutCycles) { ok = 0; break; }
+      }
+    }
+  }
+  ok = Grp::bcast(ok, 0);
+  return ok != 0;
+}
+
+/* unit i is finished and its bytes are visible system-wide; whoever completes a chunk tells the host */
+template <uint32_t G> __device__ __noinline__ void flow_done(const LzbFlow &f, uint32_t i, uint32_t n_units)
+{
+  typedef Group<G> Grp;
+  __threadfence_system();
+  Grp::sync();
+  if (Grp::lane() == 0)
+  {
+    const uint32_t c = i / f.chunk_units;
+    const uint32_t left = n_units - c * f.chunk_units;
+    const uint32_t count = left < f.chunk_units ? left : f.chunk_units;
+    if (atomicAdd(f.done + c, 1u) + 1u == count)
+    {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" : : "l"(f.ready + c), "r"(1u) : "memory");
+    }
+  }
+  Grp::sync();
+}
+
+template <bool kSharedModel, uint32_t G, bool kFlow>
 __global__ void __launch_bounds__(max_warps_for(G) * 32, 1)
 lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict__ out,
                         const LzbUnit *__restrict__ units, LzbResult *__restrict__ results, uint32_t n_units,
-                        uint32_t *ticket, uint32_t region_bytes, uint32_t slab_stride, uint8_t *model_slab)
+                        uint32_t *ticket, uint32_t region_bytes, uint32_t slab_stride, uint8_t *model_slab, const LzbFlow flow)
 {
   extern __shared__ __align__(16) uint8_t lzb_smem[];
   typedef Group<G> Grp;
@@ -60,6 +115,17 @@ lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict_
       if (Grp::lane() == 0) i = atomicAdd(ticket, 1u);
       i = Grp::bcast(i, 0);
       if (i >= n_units) d.st = S_EXIT;
+      else if (kFlow && flow.arrived && !flow_wait<G>(flow, i))
+      {
+        /* the input never came (host gave up or timed out): answer and move on, never hang */
+        if (Grp::lane() == 0)
+        {
+          LzbResult r;
+          r.res = LZB_SZ_ERROR_FAIL; r.status = LZB_ST_NOT_SPECIFIED; r.src_used = 0; r.dst_done = 0; r.check = 0;
+          results[i] = r;
+        }
+        flow_done<G>(flow, i, n_units);
+      }
       else
       {
         ui = i;
@@ -81,6 +147,7 @@ lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict_
         if (!(u.flags & LZB_UNIT_STATEFUL)) post_process<G>(u, r, dst, region, reinterpret_cast<uint8_t *>(matched));
         if (Grp::lane() == 0) results[ui] = r;
         Grp::sync();
+        if (kFlow && flow.done) flow_done<G>(flow, ui, n_units);
         d.st = S_FETCH;
       }
     }
@@ -198,21 +265,31 @@ extern "C" int lzb_launch_geometry(uint32_t smem_model_bytes, uint32_t gmem_mode
   return 0;
 }
 
-template <bool kShared, uint32_t G>
-static cudaError_t launch_variant(const LzbGeometry &g, uint32_t ctas, const uint8_t *d_packed, uint8_t *d_out,
+template <bool kShared, uint32_t G, bool kFlow>
+static cudaError_t launch_variant2(const LzbGeometry &g, uint32_t ctas, const uint8_t *d_packed, uint8_t *d_out,
                                   const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units, uint32_t *d_ticket,
-                                  uint8_t *d_slab, cudaStream_t stream)
+                                  uint8_t *d_slab, const LzbFlow &flow, cudaStream_t stream)
 {
   const size_t smem = kShared ? (size_t)g.units_per_cta * g.region_bytes : 0;
   if (kShared)
   {
-    cudaError_t e = cudaFuncSetAttribute(lzb::lzb_decode_units_kernel<kShared, G>,
+    cudaError_t e = cudaFuncSetAttribute(lzb::lzb_decode_units_kernel<kShared, G, kFlow>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  lzb::lzb_decode_units_kernel<kShared, G><<<ctas, g.warps_per_cta * 32, smem, stream>>>(
-      d_packed, d_out, d_units, d_results, n_units, d_ticket, g.region_bytes, g.slab_stride, d_slab);
+  lzb::lzb_decode_units_kernel<kShared, G, kFlow><<<ctas, g.warps_per_cta * 32, smem, stream>>>(
+      d_packed, d_out, d_units, d_results, n_units, d_ticket, g.region_bytes, g.slab_stride, d_slab, flow);
   return cudaGetLastError();
+}
+
+/* the streamed variant is a separate instantiation: the plain launch keeps its register allocation */
+template <bool kShared, uint32_t G>
+static cudaError_t launch_variant(const LzbGeometry &g, uint32_t ctas, const uint8_t *d_packed, uint8_t *d_out,
+                                  const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units, uint32_t *d_ticket,
+                                  uint8_t *d_slab, const LzbFlow &flow, cudaStream_t stream)
+{
+  if (flow.arrived) return launch_variant2<kShared, G, true>(g, ctas, d_packed, d_out, d_units, d_results, n_units, d_ticket, d_slab, flow, stream);
+  return launch_variant2<kShared, G, false>(g, ctas, d_packed, d_out, d_units, d_results, n_units, d_ticket, d_slab, flow, stream);
 }
 
 extern "C" int lzb_launch_decode(const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *d_units,
@@ -220,6 +297,18 @@ extern "C" int lzb_launch_decode(const uint8_t *d_packed, uint8_t *d_out, const 
                                  uint32_t smem_model_bytes, uint32_t gmem_model_bytes, uint8_t *d_model_slab,
                                  cudaStream_t stream)
 {
+  return lzb_launch_decode_flow(d_packed, d_out, d_units, d_results, n_units, d_ticket, smem_model_bytes, gmem_model_bytes,
+                                d_model_slab, nullptr, stream);
+}
+
+extern "C" int lzb_launch_decode_flow(const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *d_units,
+                                      LzbResult *d_results, uint32_t n_units, uint32_t *d_ticket,
+                                      uint32_t smem_model_bytes, uint32_t gmem_model_bytes, uint8_t *d_model_slab,
+                                      const LzbFlow *flow_in, cudaStream_t stream)
+{
+  LzbFlow flow;
+  memset(&flow, 0, sizeof flow);
+  if (flow_in) flow = *flow_in;
   LzbGeometry g;
   int rc = lzb_launch_geometry(smem_model_bytes, gmem_model_bytes, &g);
   if (rc) return rc;
@@ -241,7 +330,7 @@ extern "C" int lzb_launch_decode(const uint8_t *d_packed, uint8_t *d_out, const 
   if ((uint64_t)ctas * g.units_per_cta > n_units) ctas = (n_units + g.units_per_cta - 1) / g.units_per_cta;
   cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return (int)e;
-#define LZB_LAUNCH(S, GG) launch_variant<S, GG>(g, ctas, d_packed, d_out, d_units, d_results, n_units, d_ticket, d_model_slab, stream)
+#define LZB_LAUNCH(S, GG) launch_variant<S, GG>(g, ctas, d_packed, d_out, d_units, d_results, n_units, d_ticket, d_model_slab, flow, stream)
   if (!g.shared_model) e = LZB_LAUNCH(false, 32);
   else if (g.group == 32) e = LZB_LAUNCH(true, 32);
   else if (g.group == 16) e = LZB_LAUNCH(true, 16);

@@ -31,10 +31,28 @@ typedef struct LzbGeometry
 /* Residency the decode kernel will use for a model of the given shared / HBM part sizes (bytes). */
 int lzb_launch_geometry(uint32_t smem_model_bytes, uint32_t gmem_model_bytes, LzbGeometry *g);
 
+/* A launch that is fed and drained while it runs (Lzb_DecodeUnitsHost): units are taken in index order, in
+ * chunks of chunk_units; a unit of chunk c starts once arrived[min(c+1, n_chunks-1)] is non-zero (the packed
+ * bytes are copied in chunk order by another stream, each copy followed by its flag), and the group that
+ * finishes the last unit of a chunk sets ready[c] in mapped host memory so the host can start that chunk's
+ * download.  All-null = an ordinary launch. */
+typedef struct LzbFlow
+{
+  const uint32_t *arrived;   /* device memory, n_chunks words                         */
+  uint32_t *done;            /* device memory, n_chunks counters (zeroed by the host) */
+  uint32_t *ready;           /* mapped host memory, n_chunks words                    */
+  const uint32_t *abort;     /* mapped host memory, one word: non-zero = give up      */
+  uint32_t chunk_units, n_chunks;
+} LzbFlow;
+
 /* Decode n_units units.  d_ticket: one uint32 of device scratch.  d_model_slab: g.slab_bytes bytes. */
 int lzb_launch_decode(const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *d_units, LzbResult *d_results,
                       uint32_t n_units, uint32_t *d_ticket, uint32_t smem_model_bytes, uint32_t gmem_model_bytes,
                       uint8_t *d_model_slab, cudaStream_t stream);
+
+int lzb_launch_decode_flow(const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *d_units, LzbResult *d_results,
+                           uint32_t n_units, uint32_t *d_ticket, uint32_t smem_model_bytes, uint32_t gmem_model_bytes,
+                           uint8_t *d_model_slab, const LzbFlow *flow, cudaStream_t stream);
 
 /* Filter/check only, over bytes already in device memory (dst_off/dst_cap/filter/check of each unit). */
 int lzb_launch_post_only(uint8_t *d_data, const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units,

@@ -169,14 +169,22 @@ def test_many_units_digest_of_digests(gpu, ctx, ora):
     units = lzb200.sdk.raw_lzma_units(soff, lens, doff, caps, bytes.fromhex("5d00000100"))
     units["check"], units["flags"] = R.CHECK_CRC32, R.UNIT_VERIFY
     units["expect"] = [src[i % len(src)]["plain_crc"] for i in range(n)]
-    res = lzb200.sdk.decode_units_host(ctx, packed, out, units)
-    assert (res["res"] == 0).all(), np.unique(res["res"], return_counts=True)
     want_src = np.array([src[i % len(src)]["src_len"] for i in range(n)], dtype=np.uint32)   # excludes an end mark
     want_dst = np.array([src[i % len(src)]["dest_len"] for i in range(n)], dtype=np.uint32)  # < cap when a mark ends it
-    assert (res["dst_done"] == want_dst).all() and (res["src_used"] == want_src).all()
-    assert np.bitwise_xor.reduce(res["check"]) == np.bitwise_xor.reduce(units["expect"])
-    k = 1234
-    assert zlib.crc32(out[int(doff[k]):int(doff[k]) + int(caps[k])].tobytes()) == src[k % len(src)]["plain_crc"]
+    import os
+    # both host paths: sliced launches, and ONE launch fed and drained while it runs (LzbFlow)
+    for flow in ("0", "1"):
+        os.environ["LZB_FLOW"] = flow
+        try:
+            out[:] = 0
+            res = lzb200.sdk.decode_units_host(ctx, packed, out, units)
+        finally:
+            os.environ.pop("LZB_FLOW", None)
+        assert (res["res"] == 0).all(), (flow, np.unique(res["res"], return_counts=True))
+        assert (res["dst_done"] == want_dst).all() and (res["src_used"] == want_src).all(), flow
+        assert np.bitwise_xor.reduce(res["check"]) == np.bitwise_xor.reduce(units["expect"]), flow
+        for k in (0, 1234, n - 1):
+            assert zlib.crc32(out[int(doff[k]):int(doff[k]) + int(caps[k])].tobytes()) == src[k % len(src)]["plain_crc"], (flow, k)
     lzb200.sdk.pinned_free_all()
 
 

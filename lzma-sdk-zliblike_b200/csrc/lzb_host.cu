@@ -271,6 +271,7 @@ static SRes decode_units_flow(LzbContext *c, const Byte *packed, size_t packedBy
                               const LzbUnit *units, LzbResult *results, size_t n, const ModelBytes &model, size_t slab,
                               uint64_t total_out)
 {
+  const auto t_entry = std::chrono::steady_clock::now();
   size_t chunk_units = (size_t)std::max<uint64_t>(1, (uint64_t)n * kFlowChunkBytes / std::max<uint64_t>(total_out, 1));
   if (chunk_units > n) chunk_units = n;
   while ((n + chunk_units - 1) / chunk_units > kFlowMaxChunks) chunk_units *= 2;
@@ -355,6 +356,9 @@ static SRes decode_units_flow(LzbContext *c, const Byte *packed, size_t packedBy
   if (trace) fprintf(stderr, "[flow] download stream idle at %.2f ms\n", ms_since());
   if (!ok) return SZ_ERROR_FAIL;
   memcpy(results, s.h_results, n * sizeof(LzbResult));
+  if (trace) fprintf(stderr, "[flow] call took %.2f ms (%.2f ms before the first poll)\n",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(),
+                     std::chrono::duration<double, std::milli>(t_start - t_entry).count());
   return ret;
 }
 

@@ -35,7 +35,7 @@ constexpr long long kFlowTimeoutCycles = 20000000000ll;        /* ~10 s at 2 GHz
 
 /* wait until unit i's packed bytes (and the chunk after them: a 32-byte sector may straddle the boundary, and
  * L1 must never see a sector before all of it has landed) are in device memory; false = give up */
-template <uint32_t G> __device__ __noinline__ bool flow_wait(const LzbFlow &f, uint32_t i)
+template <uint32_t G> __device__ __forceinline__ bool flow_wait(const LzbFlow &f, uint32_t i)
 {
   typedef Group<G> Grp;
   const uint32_t c = i / f.chunk_units;
@@ -65,7 +65,7 @@ template <uint32_t G> __device__ __noinline__ bool flow_wait(const LzbFlow &f, u
 }
 
 /* unit i is finished and its bytes are visible system-wide; whoever completes a chunk tells the host */
-template <uint32_t G> __device__ __noinline__ void flow_done(const LzbFlow &f, uint32_t i, uint32_t n_units)
+template <uint32_t G> __device__ __forceinline__ void flow_done(const LzbFlow &f, uint32_t i, uint32_t n_units)
 {
   typedef Group<G> Grp;
   __threadfence_system();
@@ -195,6 +195,12 @@ lzb_sha256_kernel(const uint8_t *__restrict__ data, LzbShaJob *jobs, uint32_t n_
 }  // namespace lzb
 
 /* ------------------------------------------------------------------ launchers (C linkage) ------ */
+static uint32_t env_u32(const char *name, uint32_t dflt)
+{
+  const char *v = getenv(name);
+  return (v && atoi(v) > 0) ? (uint32_t)atoi(v) : dflt;
+}
+
 static int g_dev_sms = 0;
 static size_t g_dev_smem_optin = 0;
 
@@ -213,11 +219,6 @@ static cudaError_t query_device()
   return cudaSuccess;
 }
 
-static uint32_t env_u32(const char *name, uint32_t dflt)
-{
-  const char *v = getenv(name);
-  return (v && atoi(v) > 0) ? (uint32_t)atoi(v) : dflt;
-}
 
 extern "C" int lzb_launch_geometry(uint32_t smem_model_bytes, uint32_t gmem_model_bytes, LzbGeometry *g)
 {
@@ -282,7 +283,8 @@ static cudaError_t launch_variant2(const LzbGeometry &g, uint32_t ctas, const ui
   return cudaGetLastError();
 }
 
-/* the streamed variant is a separate instantiation: the plain launch keeps its register allocation */
+/* the streamed variant is a separate instantiation: the plain launch keeps its register allocation (the
+ * schedule ptxas finds is sensitive: with the two flow helpers out of line the same loop ran 3 % slower) */
 template <bool kShared, uint32_t G>
 static cudaError_t launch_variant(const LzbGeometry &g, uint32_t ctas, const uint8_t *d_packed, uint8_t *d_out,
                                   const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units, uint32_t *d_ticket,

@@ -389,6 +389,43 @@ def main():
                    ms_per_step=dt / a.steps * 1e3, per_call_ms=[round(x, 2) for x in per_call], verified=e2e_ok,
                    api="Lzb_DecodeUnitsHost (pinned host arenas; one launch fed and drained while it runs)")
 
+    # ---------------- xz4m only: the same blocks as ONE real .xz file through the container API (rank 0)
+    container = None
+    if a.workload == "xz4m" and not a.no_e2e and rank == 0 and world == 1:
+        from oracle import refbind
+        if refbind.have_ref():
+            ref = refbind.ref()
+            nb = n_units
+            idx = t["idx"][:nb]
+            ustart = np.concatenate(([0], np.cumsum(w["plen"].astype(np.uint64))[:-1]))
+            plen = w["plen"][idx].astype(np.uint32)
+            poff = np.concatenate(([0], np.cumsum(plen.astype(np.uint64))[:-1])).astype(np.uint64)
+            blob = np.concatenate([w["blob"][int(ustart[k]):int(ustart[k]) + int(w["plen"][k])] for k in idx])
+            xz = ref.xz_assemble(blob, poff, plen, w["ulen"][idx].astype(np.uint32), w["crc64"][idx], 4, 4, 0, int(w["props"][0]))
+            total = int(w["ulen"][idx].astype(np.uint64).sum())
+            hx = lzb200.sdk.pinned_empty(len(xz)); hx[:] = xz
+            ho = lzb200.sdk.pinned_empty(total + 16)
+            times = []
+            for i in range(2 + a.steps):
+                tc = time.perf_counter()
+                d = lzb200.sdk.xz_decode(hx, total, ctx, out=ho)
+                if i >= 2:
+                    times.append(time.perf_counter() - tc)
+            okc = d["res"] == 0 and d["finished"] and d["dest_len"] == total and d["num_blocks"] == nb and \
+                zlib.crc32(d["out"][:int(w["ulen"][idx[0]])].tobytes()) == int(w["crc32"][idx[0]])
+            # the reference on one thread: timed on the first 32 blocks as a file of their own (bounded sample)
+            ns = min(nb, 32)
+            xs = ref.xz_assemble(blob[: int(poff[ns - 1]) + int(plen[ns - 1])], poff[:ns], plen[:ns], w["ulen"][idx[:ns]].astype(np.uint32),
+                                 w["crc64"][idx[:ns]], 4, 4, 0, int(w["props"][0]))
+            tot_s = int(w["ulen"][idx[:ns]].astype(np.uint64).sum())
+            t1 = time.perf_counter()
+            rr = ref.xz_decode(xs, tot_s)
+            cpu1 = time.perf_counter() - t1
+            container = dict(api="XzDecodeParallel on one .xz file (host buffers; framing on the host, all blocks in one GPU pass)",
+                             blocks=nb, file_bytes=int(len(xz)), out_bytes=total, value=total / float(np.mean(times)) / 1e9, unit="GB/s",
+                             verified=bool(okc), reference_one_thread=dict(value=tot_s / cpu1 / 1e9, unit="GB/s", res=int(rr["res"]), blocks=ns,
+                             note="the reference decodes one .xz file on one thread (XzUnpacker_Code loop)"))
+
     # ---------------- roofline of the dominant kernel (the fused decode launch = the whole step)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -433,6 +470,8 @@ def main():
                     data="synthetic", config=cfg, clocks=clocks, e2e=e2e, gpu_launches=a.steps, roofline=roofline,
                     cpu_baseline=cpu, verified=verified,
                     ratio=dict(packed_over_unpacked=t["sum_p"] / t["sum_u"]))
+        if container:
+            line["container_e2e"] = container
         print(json.dumps(line))
     if dist:
         dist.barrier()

@@ -93,11 +93,12 @@ def lzma2_decode(packed, prop: int, dest_cap: int, finish_mode: int = R.LZMA_FIN
 
 
 # ----------------------------------------------------------------------------- xz
-def xz_decode(data, dest_cap: int, ctx=None) -> dict:
-    """Whole-buffer XzUnpacker_Code contract (reference Xz.h:223-246)."""
+def xz_decode(data, dest_cap: int, ctx=None, out=None) -> dict:
+    """Whole-buffer XzUnpacker_Code contract (reference Xz.h:223-246).  out: optional preallocated (pinned) buffer."""
     L = _lib.load()
     src = _u8(data)
-    dst = np.zeros(max(dest_cap, 1), dtype=np.uint8)
+    dst = out if out is not None else np.zeros(max(dest_cap, 1), dtype=np.uint8)
+    assert dst.dtype == np.uint8 and dst.size >= dest_cap
     dl, sl, st = C.c_size_t(dest_cap), C.c_size_t(len(src)), C.c_int(0)
     nb, fin = C.c_uint64(0), C.c_int(0)
     r = L.XzDecodeParallel(ctx.h if ctx else None, _p(dst), C.byref(dl), _p(src), C.byref(sl), C.byref(st),

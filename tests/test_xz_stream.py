@@ -68,7 +68,7 @@ def product():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("blob", ["xz0", "xz1", "xz2", "xz3", "sha_x86", "sha_two_streams", "tiny_crc64", "empty",
-                                  "small_x86_crc32"])
+                                  "small_x86_crc32", "f_arm", "f_armt", "f_ppc", "f_sparc", "f_ia64", "chain3"])
 def test_product_matches_golden_traces(product, blob):
     cases, blobs = golden()
     mine = [c for c in cases if c["blob"] == blob]

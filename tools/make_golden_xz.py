@@ -73,6 +73,19 @@ def new_blobs():
     d = add_x86_callsites(corpus[510000:530000], seed=9).tobytes()
     blobs["small_x86_crc32"] = lzma.compress(d, format=lzma.FORMAT_XZ, check=lzma.CHECK_CRC32, filters=x86_l2)
     plains["small_x86_crc32"] = d
+    # the other branch converters and a three-filter chain (liblzma writes them, the reference reads them)
+    from tools.make_golden_bra import synth
+    for name, fid, arch in (("f_arm", lzma.FILTER_ARM, "arm"), ("f_armt", lzma.FILTER_ARMTHUMB, "armt"), ("f_ppc", lzma.FILTER_POWERPC, "ppc"),
+                            ("f_sparc", lzma.FILTER_SPARC, "sparc"), ("f_ia64", lzma.FILTER_IA64, "ia64")):
+        data = np.concatenate((synth(arch, 150000, seed=7), corpus[540000:560000])).tobytes()
+        blobs[name] = lzma.compress(data, format=lzma.FORMAT_XZ, check=lzma.CHECK_CRC64,
+                                    filters=[{"id": fid}, {"id": lzma.FILTER_LZMA2, "preset": 1, "dict_size": 1 << 18}])
+        plains[name] = data
+    data = add_x86_callsites(corpus[560000:700000], seed=12).tobytes()
+    blobs["chain3"] = lzma.compress(data, format=lzma.FORMAT_XZ, check=lzma.CHECK_CRC32,
+                                    filters=[{"id": lzma.FILTER_DELTA, "dist": 4}, {"id": lzma.FILTER_X86},
+                                             {"id": lzma.FILTER_LZMA2, "preset": 1, "dict_size": 1 << 18}])
+    plains["chain3"] = data
     return blobs, plains
 
 

@@ -12,6 +12,15 @@
  * (8 KiB, touched once per match) live in an L2-resident HBM slab.  With K units
  * per warp only units/K warps need registers: the default is G = 16, 18 warps, 36 units per SM.
  * Models whose shared part exceeds 56 KiB (raw LZMA with lc+lp >= 6) live entirely in the slab.
+ *
+ * Streaming.  The <..., kFlow = true> instantiation is the same loop for a launch that is fed and drained while
+ * it runs (LzbFlow, lzb_kernels.h; host side: decode_units_flow in lzb_host.cu): a group waits for the arrival
+ * flag of its unit's chunk before it starts the unit, and the group that completes a chunk raises a flag in
+ * mapped host memory.
+ *
+ *   lzb_post_only_kernel : filter / check over bytes already in device memory (stand-alone x86_Convert,
+ *       ARM/ARMT/PPC/SPARC/IA64_Convert, Delta_*, Crc* calls; block- and file-level passes of xz and 7z).
+ *   lzb_sha256_kernel    : xz block check 10, one thread per digest.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -236,6 +236,7 @@ static void make_slices(const LzbUnit *u, size_t n, size_t min_units, std::vecto
  * for a unit's chunk, and the group that completes a chunk raises a flag in mapped host memory, on which this
  * thread starts the chunk's download on a third stream.  Compared with sliced launches there is no per-slice
  * drain (a unit takes tens of milliseconds) and the copies of the first and last slice are not exposed. */
+#define LZB_FLOW_STALLED (-1000)
 static const uint64_t kFlowChunkBytes = 32ull << 20;
 static const size_t kFlowMaxChunks = 8192;
 
@@ -293,10 +294,9 @@ static SRes decode_units_flow(LzbContext *c, const Byte *packed, size_t packedBy
             lzb_cuda_ok(cudaStreamWaitEvent(s_up, c->flow_event, 0), "flow wait") &&
             lzb_cuda_ok(cudaMemcpyAsync(s.d_units, units, n * sizeof(LzbUnit), cudaMemcpyHostToDevice, s_run), "H2D units");
   if (!ok) return SZ_ERROR_FAIL;
-  int rc = lzb_launch_decode_flow(s.d_packed, s.d_out, s.d_units, s.d_results, (uint32_t)n, s.d_ticket, model.smem, model.gmem,
-                                  s.d_slab, &flow, s_run);
-  if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
-  /* feed: chunk k's packed bytes, then its flag (stream order = arrival order) */
+  /* feed: chunk k's packed bytes, then its flag (stream order = arrival order).  Enqueued BEFORE the launch: a
+   * launch call that blocks until the kernel ends (a profiler does that) must not leave the kernel waiting
+   * for copies nobody has asked for yet */
   for (size_t k = 0; k < n_chunks && ok; k++)
   {
     const size_t a = k * chunk_units, b = std::min(n, a + chunk_units);
@@ -304,6 +304,10 @@ static SRes decode_units_flow(LzbContext *c, const Byte *packed, size_t packedBy
     if (hi > lo) ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_packed + lo, packed + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s_up), "H2D packed chunk");
     ok = ok && lzb_cuda_ok(cudaMemcpyAsync(d_arrived + k, c->h_one, sizeof(uint32_t), cudaMemcpyHostToDevice, s_up), "H2D arrival flag");
   }
+  int rc = lzb_launch_decode_flow(s.d_packed, s.d_out, s.d_units, s.d_results, (uint32_t)n, s.d_ticket, model.smem, model.gmem,
+                                  s.d_slab, &flow, s_run);
+  if (!ok) { *h_abort = 1; }
+  if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
   /* drain: as chunks complete */
   const bool trace = getenv("LZB_FLOW_TRACE") != nullptr;
   const auto t_start = std::chrono::steady_clock::now();
@@ -311,14 +315,22 @@ static SRes decode_units_flow(LzbContext *c, const Byte *packed, size_t packedBy
   if (trace) fprintf(stderr, "[flow] %zu units, %zu chunks of %zu units; fed at %.2f ms\n", n, n_chunks, chunk_units, ms_since());
   SRes ret = ok ? SZ_OK : SZ_ERROR_FAIL;
   if (!ok) *h_abort = 1;
-  bool up_logged = false;
-  if (trace) cudaEventRecord(c->flow_event, s_up);
+  bool up_done = false, stalled = false;
+  if (ok) cudaEventRecord(c->flow_event, s_up);         /* (its first use, ordering the flag reset, is over) */
   for (size_t k = 0; k < n_chunks && ret == SZ_OK; k++)
   {
     unsigned idle = 0;
     while (h_ready[k] == 0)
     {
-      if (trace && !up_logged && cudaEventQuery(c->flow_event) == cudaSuccess) { up_logged = true; fprintf(stderr, "[flow] uploads complete at %.2f ms\n", ms_since()); }
+      if (!up_done && cudaEventQuery(c->flow_event) == cudaSuccess)
+      {
+        up_done = true;
+        if (trace) fprintf(stderr, "[flow] uploads complete at %.2f ms\n", ms_since());
+      }
+      /* watchdog: copies that do not progress next to the running kernel (a profiler serialising the device,
+       * a platform without concurrent copy) would leave every group waiting for its input: give up early, the
+       * caller repeats the call with sliced launches and stops using streamed ones */
+      if (k == 0 && !up_done && ms_since() > 2000.0) { stalled = true; ret = SZ_ERROR_FAIL; break; }
       if ((++idle & 1023u) == 0)
       {
         /* the kernel ending (or failing) without the flag means something went wrong on the device */
@@ -355,6 +367,7 @@ static SRes decode_units_flow(LzbContext *c, const Byte *packed, size_t packedBy
   ok = lzb_cuda_ok(cudaStreamSynchronize(s_down), "download stream") && ok;
   if (trace) fprintf(stderr, "[flow] download stream idle at %.2f ms\n", ms_since());
   if (!ok) return SZ_ERROR_FAIL;
+  if (stalled) { lzb_set_error("streamed launch: uploads do not overlap the kernel here"); return LZB_FLOW_STALLED; }
   memcpy(results, s.h_results, n * sizeof(LzbResult));
   if (trace) fprintf(stderr, "[flow] call took %.2f ms (%.2f ms before the first poll)\n",
                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(),
@@ -383,13 +396,25 @@ extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t pa
   {
     size_t free_b = 0, total_b = 0;
     const char *mode = getenv("LZB_FLOW");
-    const bool want = mode ? atoi(mode) != 0 : total_out >= (256ull << 20);
-    if (want && n < 0xFFFFFFFFull && flow_layout_ok(units, n) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+    const bool want = !c->flow_off && (mode ? atoi(mode) != 0 : total_out >= (256ull << 20));
+    /* page-locked arenas only: copies from pageable memory block the calling thread, which must stay free to
+     * feed and drain the launch */
+    auto pinned = [](const void *p) {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+      return a.type == cudaMemoryTypeHost;
+    };
+    if (want && n < 0xFFFFFFFFull && pinned(packed) && pinned(out) && flow_layout_ok(units, n) &&
+        cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
     {
       const LzbSlot &s0 = c->slot[0];
       const uint64_t have = (uint64_t)free_b + s0.packed_cap + s0.out_cap;
       if ((uint64_t)packedBytes + outBytes + (1ull << 30) < have)
-        return decode_units_flow(c, packed, packedBytes, out, outBytes, units, results, n, model, slab, total_out);
+      {
+        const SRes r = decode_units_flow(c, packed, packedBytes, out, outBytes, units, results, n, model, slab, total_out);
+        if (r != LZB_FLOW_STALLED) return r;
+        c->flow_off = true;                              /* sticky: sliced launches from here on */
+      }
     }
   }
   std::vector<Slice> slices;

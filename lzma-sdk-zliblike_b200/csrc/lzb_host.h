@@ -38,6 +38,7 @@ struct LzbContext
   uint32_t *d_flow = nullptr; uint32_t *h_flow = nullptr; uint32_t *h_flow_dev = nullptr; size_t flow_cap = 0;
   uint32_t *h_one = nullptr;
   cudaEvent_t flow_event = nullptr;
+  bool flow_off = false;            /* uploads did not overlap a running kernel once: use sliced launches */
   std::mutex mu;
 };
 

@@ -40,7 +40,7 @@ namespace lzb {
 constexpr uint32_t max_warps_for(uint32_t G) { return G == 32 ? 16u : (G == 16 ? 18u : 8u); }
 
 /* ---- a launch that is fed and drained while it runs (LzbFlow, lzb_kernels.h) ---- */
-constexpr long long kFlowTimeoutCycles = 20000000000ll;        /* ~10 s at 2 GHz */
+constexpr long long kFlowTimeoutCycles = 8000000000ll;         /* ~4 s at 2 GHz */
 
 /* wait until unit i's packed bytes (and the chunk after them: a 32-byte sector may straddle the boundary, and
  * L1 must never see a sector before all of it has landed) are in device memory; false = give up */

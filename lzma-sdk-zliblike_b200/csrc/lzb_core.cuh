@@ -433,25 +433,28 @@ template <uint32_t G> struct UnitDecoderT
    * kept in terms of the node's 32-bit shared-memory BYTE address A (node m of a tree at L: A = L + 2m):
    * the child address is 2A + (bit ? 2 - L : -L), one select inside the bit step + one multiply-add, where
    * index arithmetic on m needs four instructions.  80 % of all decoded bits are of this kind (profiles/). */
-  LZB_FN uint32_t literal_plain(uint16_t *lit)
+  LZB_FN uint32_t literal_plain(uint16_t *lit) { return tree_walk<8>(lit); }
+
+  /* BITS steps down a binary tree stored as t[1 .. 2^BITS): returns the node index reached (leading 1 bit kept) */
+  template <int BITS> LZB_FN uint32_t tree_walk(uint16_t *lit)
   {
 #ifdef LZB_EMU
     uint32_t sym = 1;
-    for (int i = 0; i < 8; i++) sym = (sym << 1) | rc_bit(lit + sym);
+    for (int i = 0; i < BITS; i++) sym = (sym << 1) | rc_bit(lit + sym);
     return sym;
 #else
     if (!probs_in_smem)
     {
       uint32_t sym = 1;
 #pragma unroll 1
-      for (int i = 0; i < 8; i++) sym = (sym << 1) | rc_bit(lit + sym);
+      for (int i = 0; i < BITS; i++) sym = (sym << 1) | rc_bit(lit + sym);
       return sym;
     }
     const uint32_t L = (uint32_t)__cvta_generic_to_shared(lit);
     const uint32_t k0 = 0u - L, k1 = 2u - L;
     uint32_t A = L + 2;
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < BITS; i++)
     {
       uint32_t pr, np, c;
       asm volatile("ld.shared.u16 %0, [%1];" : "=r"(pr) : "r"(A) : "memory");
@@ -491,13 +494,7 @@ template <uint32_t G> struct UnitDecoderT
     return neg + 1u;
   }
 
-  template <int BITS> LZB_FN uint32_t tree_msb(uint16_t *t)
-  {
-    uint32_t m = 1;
-#pragma unroll
-    for (int i = 0; i < BITS; i++) m = (m << 1) | rc_bit(t + m);
-    return m - (1u << BITS);
-  }
+  template <int BITS> LZB_FN uint32_t tree_msb(uint16_t *t) { return tree_walk<BITS>(t) - (1u << BITS); }
 
   LZB_FN uint32_t tree_lsb(uint16_t *t, uint32_t bits)
   {

@@ -76,10 +76,6 @@ constexpr uint32_t oVar = 950;               /* pb-dependent part starts here: *
 
 enum { kSymLit = 0, kSymMatch = 1, kSymRep = 2, kSymStarved = 3 };
 
-/* micro-states of the bit machine, and what a finished tree walk was for */
-enum { MS_ISMATCH = 0, MS_TREE, MS_ISREP, MS_G0, MS_REP0LONG, MS_G1, MS_G2, MS_CHOICE, MS_CHOICE2 };
-enum { C_LIT = 0, C_LEN_LOW, C_LEN_MID, C_LEN_HIGH, C_SLOT };
-
 /* states of the per-unit driver machine */
 enum { S_FETCH = 0, S_L2_TOP, S_TD_ENTER, S_TD_TOP, S_SPAN_TOP, S_RUN, S_AFTER_RUN, S_TD_RET, S_UNIT_END, S_EXIT };
 /* LZMA2 header phases == ELzma2State (Lzma2Dec.c:47-59): it is what CLzma2Dec.state holds between calls */
@@ -315,13 +311,6 @@ template <uint32_t G> struct UnitDecoderT
   uint32_t peek_byte;      /* dic[dicPos-rep0], valid while state >= 7 (matched literal) */
   bool want_rc_init, want_state_init;
   uint32_t held_out;       /* input bytes parked for the next call (CLzmaDec.tempBufSize) when starved */
-
-  /* bit machine (step_bit): the unit's position INSIDE a symbol, so that the units of a warp can share the
-   * bit-decode instructions whatever symbols they are in */
-  uint32_t ms;             /* MS_*: what the bit about to be decoded means                                   */
-  uint32_t paddr;          /* where its probability lives: byte address in the shared-memory model           */
-  uint32_t tree;           /* MS_TREE: steps left (bits 0-7), what the finished walk is (C_*, bits 8-15), length (16+) */
-  uint32_t tk0, tk1;       /* MS_TREE: child address = 2 * paddr + (bit ? tk1 : tk0), tk0 = -base, tk1 = 2 - base */
 
   /* driver machine */
   uint32_t st;             /* S_* */
@@ -749,289 +738,21 @@ template <uint32_t G> struct UnitDecoderT
     return 0;
   }
 
-  /* ---------------- the bit machine ----------------
-   * decode_symbol above decodes one whole symbol per call; the K units of a warp are then rarely in the same
-   * symbol, and the warp pays for every distinct path.  Here one call decodes ONE modelled bit -- the same
-   * dozen instructions whatever the bit means -- and then moves the unit's micro-state; units that are in
-   * different symbols still share the bit decode, and while they walk trees (literals: 8 of 9 bits) also the
-   * state update.  Rare pieces (matched literal, reverse trees, direct bits, the copy) run inside a transition.
-   * Same grammar, same arithmetic, same order of probability updates as decode_symbol (LzmaDec.c:153-410). */
-  LZB_FN uint32_t prob_base() const
-  {
-#ifdef LZB_EMU
-    return 0;                                        /* addresses are byte offsets into `probs` */
-#else
-    return (uint32_t)__cvta_generic_to_shared(probs);
-#endif
-  }
-  LZB_FN uint32_t PA(uint32_t entry) const { return prob_base() + (entry << 1); }
-
-  /* one modelled bit at model address a; returns bit ? k1 : k0 */
-  LZB_FN uint32_t bit_at(uint32_t a, uint32_t k0, uint32_t k1)
-  {
-#ifdef LZB_EMU
-    uint16_t *p = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(probs) + a);
-    return rc_bit(p) ? k1 : k0;
-#else
-    uint32_t pr, np, c;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(pr) : "r"(a) : "memory");
-    rc_norm();
-    asm("{\n\t"
-        ".reg .pred q;\n\t"
-        ".reg .u32 b, t, k;\n\t"
-        "shr.u32 b, %0, 11;\n\t"
-        "mul.lo.u32 b, b, %4;\n\t"
-        "setp.ge.u32 q, %1, b;\n\t"
-        "sub.u32 t, %0, b;\n\t"
-        "selp.u32 %0, t, b, q;\n\t"
-        "@q sub.u32 %1, %1, b;\n\t"
-        "selp.u32 %2, %6, %5, q;\n\t"
-        "selp.u32 k, 0, 2017, q;\n\t"
-        "sub.u32 k, %4, k;\n\t"
-        "shr.s32 k, k, 5;\n\t"
-        "sub.u32 %3, %4, k;\n\t"
-        "}"
-        : "+r"(range), "+r"(code), "=r"(c), "=r"(np)
-        : "r"(pr), "r"(k0), "r"(k1));
-    asm volatile("st.shared.u16 [%0], %1;" : : "r"(a), "r"(np) : "memory");
-    return c;
-#endif
-  }
-
-  LZB_FN void begin_symbol()
-  {
-    ms = MS_ISMATCH;
-    paddr = PA(oVar + (state << pb) + (total_pos & pb_mask));
-  }
-
-  /* start a walk of `bits` steps down the tree at entry index `root` (node 1 is its first node) */
-  LZB_FN void begin_tree(uint32_t root, uint32_t bits, uint32_t what)
-  {
-    const uint32_t base = PA(root);
-    tk0 = 0u - base; tk1 = 2u - base;
-    paddr = base + 2;
-    tree = bits | (what << 8);
-    ms = MS_TREE;
-  }
-
-  LZB_FN void begin_len() { ms = MS_CHOICE; paddr = PA(oLenChoice + (state < 12 ? 2u : 0u)); }
-
-  LZB_FN void emit_literal(uint32_t byte)
-  {
-    prev_byte = byte;
-    if (Grp::lane() == 0) dic[dic_pos] = (uint8_t)byte;
-    dic_pos++;
-    total_pos++;
-  }
-
-  /* the copy that ends a match / rep (LzmaDec.c:376-408); 1 = symbol done, 2 = error */
-  LZB_FN int finish_match(uint32_t len, uint32_t limit, uint32_t &left_over)
-  {
-    len += 2;
-    if (limit == dic_pos) return 2;                                           /* :378-379 */
-    const uint32_t room = limit - dic_pos;
-    const uint32_t cur = room < len ? room : len;
-    left_over = len - cur;
-    copy_from_window(cur);
-    return 1;
-  }
-
-  /* returns 0: symbol not finished, 1: symbol finished, 2: data error, 3: end marker */
-  LZB_FN int step_bit(uint32_t limit, uint32_t &left_over)
-  {
-    const uint32_t c = bit_at(paddr, tk0, tk1);
-    if (ms == MS_TREE)
-    {
-      paddr = paddr * 2 + c;
-      tree -= 1;
-      if ((tree & 0xFFu) != 0) return 0;
-      const uint32_t node = (paddr + tk0) >> 1;               /* index in the tree, leading 1 included */
-      const uint32_t what = (tree >> 8) & 0xFFu;
-      if (what == C_LIT) { emit_literal(node & 0xFFu); return 1; }
-      uint32_t len;
-      if (what == C_SLOT)
-      {
-        /* ---- distance, :294-374: the slot is known, the rest of it is decoded right here ---- */
-        uint16_t *const P = probs;
-        len = tree >> 16;                                      /* parked there by the length walk below */
-        uint32_t dist = node - 64;
-        if (dist >= 4)
-        {
-          const uint32_t slot = dist;
-          uint32_t nbits = (slot >> 1) - 1;
-          dist = 2 | (slot & 1);
-          if (slot < 14)
-          {
-            dist <<= nbits;
-            dist |= tree_lsb(P + oDistSpec + dist - slot - 1, nbits);
-          }
-          else
-          {
-            nbits -= 4;
-            do { dist = (dist << 1) + rc_direct(); } while (--nbits != 0);
-            dist <<= 4;
-            dist |= tree_lsb(P + oDistAlign, 4);
-            if (dist == 0xFFFFFFFFu)
-            {
-              left_over = len + kEndMarkLen;                   /* end marker, :354-359 */
-              state -= 12;
-              return 3;
-            }
-          }
-        }
-        rep3 = rep2; rep2 = rep1; rep1 = rep0;
-        rep0 = dist + 1;
-        if (dict_full == 0 ? dist >= total_pos : dist >= dict_full) return 2;    /* :366-372 */
-        state = (state < 12 + 7) ? 7 : 10;
-        return finish_match(len, limit, left_over);
-      }
-      /* ---- a length, :261-292 ---- */
-      len = what == C_LEN_LOW ? node - 8 : (what == C_LEN_MID ? node : node - 256 + 16);
-      if (state >= 12)
-      {
-        begin_tree(oDistSlot + ((len < 4 ? len : 3u) << 6), 6, C_SLOT);
-        tree |= len << 16;                                     /* the slot walk carries the length along */
-        return 0;
-      }
-      return finish_match(len, limit, left_over);
-    }
-
-    const uint32_t bit = (c - tk0) >> 1;                       /* tk1 - tk0 == 2 always */
-    const uint32_t ps = total_pos & pb_mask;
-    switch (ms)
-    {
-      case MS_ISMATCH:
-        if (bit == 0)
-        {
-          /* ---- literal, :161-196 ---- */
-          const uint32_t ctx = ((total_pos & lp_mask) << lc) + (prev_byte >> (8 - lc));
-          const uint32_t root = oVar + (56u << pb) + (ctx << 8);
-          if (state < 7)
-          {
-            state -= (state < 4) ? state : 3;
-            begin_tree(root, 8, C_LIT);
-            return 0;
-          }
-          /* matched literal (:176-192): rare (one per match), decoded whole; see decode_symbol */
-          uint16_t *lit = probs + root, *mlit = mprobs + (ctx << 9);
-          uint32_t sym = 1, mb = peek_byte, offs = 0x100;
-          state -= (state < 10) ? 3 : 6;
-#pragma unroll 1
-          for (int i = 0; i < 8; i++)
-          {
-            mb <<= 1;
-            const uint32_t mbit = mb & offs;
-            const uint32_t b = rc_bit(offs ? mlit + mbit + sym : lit + sym);
-            sym = (sym << 1) | b;
-            offs &= b ? mbit : ~mbit;
-          }
-          emit_literal(sym & 0xFFu);
-          return 1;
-        }
-        ms = MS_ISREP; paddr = PA(oIsRep + state);
-        return 0;
-
-      case MS_ISREP:
-        if (bit == 0) { state += 12; begin_len(); return 0; }                  /* marker: "new distance follows", :204 */
-        if (dict_full == 0 && total_pos == 0) return 2;                         /* :210-211 */
-        ms = MS_G0; paddr = PA(oRepG0 + state);
-        return 0;
-
-      case MS_G0:
-        if (bit == 0) { ms = MS_REP0LONG; paddr = PA(oVar + (12u << pb) + (state << pb) + ps); }
-        else { ms = MS_G1; paddr = PA(oRepG1 + state); }
-        return 0;
-
-      case MS_REP0LONG:
-        if (bit == 0)
-        {
-          /* ---- short rep, :219-224 ---- */
-          Grp::sync();
-          const uint32_t s0 = back_index(rep0);
-          const uint8_t b = dic[s0];
-          const uint32_t s1 = (s0 + 1 == dic_size) ? 0u : s0 + 1;
-          peek_byte = (s1 == dic_pos) ? b : dic[s1];
-          prev_byte = b;
-          if (Grp::lane() == 0) dic[dic_pos] = b;
-          dic_pos++;
-          total_pos++;
-          state = state < 7 ? 9 : 11;
-          return 1;
-        }
-        state = state < 7 ? 8 : 11;
-        begin_len();
-        return 0;
-
-      case MS_G1:
-        if (bit == 0)
-        {
-          const uint32_t d = rep1;
-          rep1 = rep0; rep0 = d;
-          state = state < 7 ? 8 : 11;
-          begin_len();
-        }
-        else { ms = MS_G2; paddr = PA(oRepG2 + state); }
-        return 0;
-
-      case MS_G2:
-      {
-        uint32_t d;
-        if (bit == 0) d = rep2;
-        else { d = rep3; rep3 = rep2; }
-        rep2 = rep1; rep1 = rep0; rep0 = d;
-        state = state < 7 ? 8 : 11;
-        begin_len();
-        return 0;
-      }
-
-      case MS_CHOICE:
-      {
-        const uint32_t is_rep = state < 12 ? 1u : 0u;
-        if (bit == 0) begin_tree(oVar + (24u << pb) + ((is_rep << 3) << pb) + (ps << 3), 3, C_LEN_LOW);
-        else { ms = MS_CHOICE2; paddr = PA(oLenChoice + 2 * is_rep + 1); }
-        return 0;
-      }
-
-      default: /* MS_CHOICE2 */
-      {
-        const uint32_t is_rep = state < 12 ? 1u : 0u;
-        if (bit == 0) begin_tree(oVar + (40u << pb) + ((is_rep << 3) << pb) + (ps << 3), 3, C_LEN_MID);
-        else begin_tree(oLenHigh + (is_rep << 8), 8, C_LEN_HIGH);
-        return 0;
-      }
-    }
-  }
-
-  /* One trip of the shared loop for a unit in state S_RUN: one bit of the bit machine (shared-memory model),
-   * or one whole symbol (model in the HBM slab); after a symbol, LzmaDec_DecodeReal's loop test and epilogue
-   * (LzmaDec.c:411-423). */
+  /* One trip of the shared loop for a unit in state S_RUN: a symbol, then LzmaDec_DecodeReal's loop
+   * test and epilogue (LzmaDec.c:411-423). */
   LZB_FN void step()
   {
-    uint32_t left_over = 0;
-    int r;
-#ifndef LZB_EMU
-    if (!probs_in_smem)
-    {
-      const int q = decode_symbol(run_limit, left_over);
-      r = q == 0 ? 1 : (q == 1 ? 2 : 3);
-    }
-    else
-#endif
-    {
-      r = step_bit(run_limit, left_over);
-      if (r == 0) return;
-    }
-    if (r == 2) { run_err = true; st = S_AFTER_RUN; return; }
-    if (r == 3 || !(dic_pos < run_limit && in_pos() < run_soft))
+    uint32_t left_over;
+    const int r = decode_symbol(run_limit, left_over);
+    if (r == 1) { run_err = true; st = S_AFTER_RUN; return; }
+    if (r == 2 || !(dic_pos < run_limit && in_pos() < run_soft))
     {
       rc_norm();                                                               /* :412 */
       pending = left_over;
       dic_commit = dic_pos;
       run_err = false;
       st = S_AFTER_RUN;
-      return;
     }
-    begin_symbol();
   }
 
   /* LzmaDec.c:428-452 */
@@ -1112,7 +833,6 @@ template <uint32_t G> struct UnitDecoderT
                     uint32_t dict, uint16_t *model, uint16_t *matched_model, bool model_in_smem = false)
   {
     held_out = 0;
-    ms = MS_ISMATCH; paddr = 0; tree = 0; tk0 = 0; tk1 = 2;
     mprobs = matched_model;
     probs_in_smem = model_in_smem;
     in = packed;
@@ -1355,7 +1075,6 @@ template <uint32_t G> struct UnitDecoderT
             if (td_limit - dic_pos > room) lim = dic_pos + room;
           }
           run_limit = lim;
-          begin_symbol();
           st = S_RUN;
           return;
         }

@@ -150,6 +150,12 @@ SRes Lzma2Dec_DecodeToBuf(CLzma2Dec *p, Byte *dest, SizeT *destLen, const Byte *
 SRes Lzma2Decode(Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen, Byte prop,
                  ELzmaFinishMode finishMode, ELzmaStatus *status, ISzAlloc *alloc);
 
+/* ---- LZMA + x86 filter, one-call: reference Lzma86.h:11-12,87,107 ---- */
+#define LZMA86_SIZE_OFFSET (1 + 5)
+#define LZMA86_HEADER_SIZE (LZMA86_SIZE_OFFSET + 8)
+SRes Lzma86_GetUnpackSize(const Byte *src, SizeT srcLen, UInt64 *unpackSize);
+SRes Lzma86_Decode(Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen);
+
 /* ---- checks: reference 7zCrc.h:11-21, XzCrc64.h:13-22 ---- */
 extern UInt32 g_CrcTable[];
 extern UInt64 g_Crc64Table[];

@@ -10,8 +10,9 @@
  *                         filter and the folder CRC fused after the decode and the per-file CRCs in a second
  *                         pass over the resident output.
  * The result codes are the reference's: what SzArEx_Open returns for a damaged database, and per file what
- * SzArEx_Extract returns (folder decode error, folder CRC, file CRC).  BCJ2 folders (a serial four-stream
- * merge, 7zDec.c:308-329) and PPMd are answered with SZ_ERROR_UNSUPPORTED.
+ * SzArEx_Extract returns (folder decode error, folder CRC, file CRC).  BCJ2 folders (7zDec.c:308-329: three
+ * coders feeding a four-stream merge) decode their three streams as ordinary units and merge on the device
+ * (lzb_bcj2_kernel, one thread per folder).  PPMd (disabled in the reference) is SZ_ERROR_UNSUPPORTED.
  */
 #include "lzb_host.h"
 #include "lzb_xz.h"
@@ -30,7 +31,8 @@ enum
   kCTime, kATime, kMTime, kWinAttributes, kComment, kEncodedHeader
 };
 
-const uint64_t kMethodCopy = 0, kMethodLzma2 = 0x21, kMethodLzma = 0x30101, kMethodBcj = 0x03030103, kMethodArm = 0x03030501;
+const uint64_t kMethodCopy = 0, kMethodLzma2 = 0x21, kMethodLzma = 0x30101, kMethodBcj = 0x03030103, kMethodArm = 0x03030501,
+               kMethodBcj2 = 0x0303011B;
 
 /* bounds-checked cursor over header bytes; the first failure sticks (7zIn.c:316-400) */
 struct Cursor
@@ -346,58 +348,85 @@ SRes classify_folder(const Folder &f, LzbSzFolder &o)
     else return SZ_ERROR_UNSUPPORTED;
     return SZ_OK;
   }
-  if (n == 4) lzb_set_error("7z BCJ2 folders (four-stream merge) are outside the GPU path");
+  if (n == 4)
+  {
+    const Coder &b = f.coders[3];
+    if (!main_ok(f.coders[1]) || !main_ok(f.coders[2]) || b.method != kMethodBcj2 || b.n_in != 4 || b.n_out != 1) return SZ_ERROR_UNSUPPORTED;
+    static const UInt32 want_pack[4] = { 2, 6, 1, 0 }, want_in[3] = { 5, 4, 3 };
+    if (f.pack_streams.size() != 4 || f.binds.size() != 3) return SZ_ERROR_UNSUPPORTED;
+    for (int i = 0; i < 4; i++) if (f.pack_streams[i] != want_pack[i]) return SZ_ERROR_UNSUPPORTED;
+    for (UInt32 i = 0; i < 3; i++) if (f.binds[i].in != want_in[i] || f.binds[i].out != i) return SZ_ERROR_UNSUPPORTED;
+    o.method = 3;                                          /* three coders + BCJ2 merge */
+    o.filter = 0x1B;
+    return SZ_OK;
+  }
   return SZ_ERROR_UNSUPPORTED;
 }
 
 }  // namespace
+
+/* the three coders in front of a BCJ2 merge (7zDec.c:308-329): [0] -> jump stream, [1] -> call stream,
+ * [2] -> main stream; plus the raw range-coder stream */
+struct SubCoder { uint32_t method = 0; Byte props[8] = { 0 }; uint8_t props_size = 0; UInt64 pack_off = 0, pack_size = 0, unpack_size = 0; };
+struct Bcj2Folder { SubCoder sub[3]; UInt64 rc_off = 0, rc_size = 0; };
 
 struct LzbSzArchive
 {
   std::vector<LzbSzFolder> folders;
   std::vector<LzbSzFile> files;
   std::vector<UInt16> names;
+  std::vector<Bcj2Folder> bcj2;            /* for folders with method == 3, in folder order */
+  std::vector<int> bcj2_index;             /* folder -> index in bcj2, or -1 */
   UInt64 unpack_total = 0;
 };
 
 /* one folder of the database -> the unit the kernel decodes (SzDecodeLzma / SzDecodeLzma2, 7zDec.c:126-216) */
-static SRes folder_unit(const LzbSzFolder &f, size_t archive_size, LzbUnit &u)
+static SRes coder_unit(uint32_t method, const Byte *props, unsigned props_size, UInt64 pack_off, UInt64 pack_size, UInt64 out_off,
+                       UInt64 out_size, size_t archive_size, LzbUnit &u)
 {
   memset(&u, 0, sizeof u);
-  if (f.unpack_size > 0xFFFFFFFFull || f.pack_size > 0xFFFFFFFFull) { lzb_set_error("7z folder larger than 4 GiB"); return SZ_ERROR_UNSUPPORTED; }
-  const UInt64 avail = f.pack_off >= archive_size ? 0 : std::min<UInt64>(f.pack_size, archive_size - f.pack_off);
-  u.src_off = f.pack_off; u.src_len = (uint32_t)avail;
-  u.dst_off = f.out_off; u.dst_cap = (uint32_t)f.unpack_size;
+  if (out_size > 0xFFFFFFFFull || pack_size > 0xFFFFFFFFull) { lzb_set_error("7z folder larger than 4 GiB"); return SZ_ERROR_UNSUPPORTED; }
+  const UInt64 avail = pack_off >= archive_size ? 0 : std::min<UInt64>(pack_size, archive_size - pack_off);
+  u.src_off = pack_off; u.src_len = (uint32_t)avail;
+  u.dst_off = out_off; u.dst_cap = (uint32_t)out_size;
   u.finish = LZMA_FINISH_END;
-  if (f.method == 1)
+  if (method == 1)
   {
     CLzmaProps p;
-    const SRes r = LzmaProps_Decode(&p, f.props, f.props_size);
+    const SRes r = LzmaProps_Decode(&p, props, props_size);
     if (r != SZ_OK) return r;
     u.codec = LZB_CODEC_LZMA; u.lc = (uint8_t)p.lc; u.lp = (uint8_t)p.lp; u.pb = (uint8_t)p.pb; u.dict_size = p.dicSize;
   }
   else
   {
-    if (f.props_size != 1) return SZ_ERROR_DATA;
-    if (f.props[0] > 40) return SZ_ERROR_UNSUPPORTED;
+    if (props_size != 1) return SZ_ERROR_DATA;
+    if (props[0] > 40) return SZ_ERROR_UNSUPPORTED;
     u.codec = LZB_CODEC_LZMA2;
-    u.dict_size = f.props[0] == 40 ? 0xFFFFFFFFu : ((UInt32)(2 | (f.props[0] & 1)) << (f.props[0] / 2 + 11));
+    u.dict_size = props[0] == 40 ? 0xFFFFFFFFu : ((UInt32)(2 | (props[0] & 1)) << (props[0] / 2 + 11));
   }
   return SZ_OK;
 }
 
+static SRes folder_unit(const LzbSzFolder &f, size_t archive_size, LzbUnit &u)
+{
+  return coder_unit(f.method, f.props, f.props_size, f.pack_off, f.pack_size, f.out_off, f.unpack_size, archive_size, u);
+}
+
 /* what the reference's feed loop makes of a finished decode: it hands the decoder at most 256 KiB per call,
  * and accepts the end only if the call that completed the output also used up the window it was given */
-static SRes folder_verdict(const LzbSzFolder &f, const LzbUnit &u, const LzbResult &x)
+static SRes coder_verdict(uint32_t method, UInt64 pack_size, const LzbUnit &u, const LzbResult &x);
+static SRes folder_verdict(const LzbSzFolder &f, const LzbUnit &u, const LzbResult &x) { return coder_verdict(f.method, f.pack_size, u, x); }
+
+static SRes coder_verdict(uint32_t method, UInt64 pack_size, const LzbUnit &u, const LzbResult &x)
 {
   /* decode verdict first, the folder CRC (fused into the same launch) only counts for a clean decode */
   if (x.res != SZ_OK && x.res != SZ_ERROR_CRC) return SZ_ERROR_DATA;
   if (x.dst_done != u.dst_cap) return SZ_ERROR_DATA;
-  const bool ended = x.status == LZMA_STATUS_FINISHED_WITH_MARK || (f.method == 1 && x.status == LZMA_STATUS_MAYBE_FINISHED_WITHOUT_MARK);
+  const bool ended = x.status == LZMA_STATUS_FINISHED_WITH_MARK || (method == 1 && x.status == LZMA_STATUS_MAYBE_FINISHED_WITHOUT_MARK);
   if (!ended) return SZ_ERROR_DATA;
   const UInt64 used = x.src_used, window = (UInt64)1 << 18;
   const UInt64 last_start = used == 0 ? 0 : ((used - 1) / window) * window;
-  const UInt64 last_end = std::min<UInt64>(last_start + window, f.pack_size);
+  const UInt64 last_end = std::min<UInt64>(last_start + window, pack_size);
   return used == last_end ? x.res : SZ_ERROR_DATA;
 }
 
@@ -407,12 +436,71 @@ static SRes decode_folders(LzbContext *ctx, const LzbSzArchive &a, const Byte *a
   const size_t nf = a.folders.size();
   std::vector<LzbUnit> units, post_a, post_b;
   std::vector<size_t> unit_folder, a_folder, b_file;
+  std::vector<int> unit_sub;                            /* -1: the folder's only coder; 0..2: coder in front of a BCJ2 merge */
   std::vector<LzbCopyRange> copies;
+  std::vector<LzbBcj2Job> jobs;
+  std::vector<size_t> job_folder;
+  UInt64 scratch = (out_bytes + 15) & ~(UInt64)15;      /* call / jump streams of BCJ2 folders live behind the output */
   for (size_t i = 0; i < nf; i++)
   {
     const LzbSzFolder &f = a.folders[i];
     folder_res[i] = (SRes)f.supported;
     if (folder_res[i] != SZ_OK) continue;
+    if (f.method == 3)
+    {
+      /* 7zDec.c:348-430 for the four-coder chain: coder 0 -> jump stream, 1 -> call stream (both scratch),
+       * 2 -> main stream at the END of the folder's output, then the merge in place */
+      if (i >= a.bcj2_index.size() || a.bcj2_index[i] < 0) { folder_res[i] = SZ_ERROR_UNSUPPORTED; continue; }
+      const Bcj2Folder &b = a.bcj2[(size_t)a.bcj2_index[i]];
+      if (b.sub[2].unpack_size > f.unpack_size) { folder_res[i] = SZ_ERROR_PARAM; continue; }
+      UInt64 where[3];
+      where[0] = scratch; scratch += (b.sub[0].unpack_size + 15) & ~(UInt64)15;
+      where[1] = scratch; scratch += (b.sub[1].unpack_size + 15) & ~(UInt64)15;
+      where[2] = f.out_off + (f.unpack_size - b.sub[2].unpack_size);
+      SRes r = SZ_OK;
+      const size_t units_before = units.size(), copies_before = copies.size();
+      for (int ci = 0; ci < 3 && r == SZ_OK; ci++)
+      {
+        const SubCoder &sc = b.sub[ci];
+        if (sc.method == 0)
+        {
+          if (sc.pack_size != sc.unpack_size) r = SZ_ERROR_DATA;
+          else if (sc.pack_off + sc.pack_size > size) r = SZ_ERROR_INPUT_EOF;
+          else copies.push_back({ sc.pack_off, where[ci], sc.pack_size });
+        }
+        else
+        {
+          LzbUnit u;
+          r = coder_unit(sc.method, sc.props, sc.props_size, sc.pack_off, sc.pack_size, where[ci], sc.unpack_size, size, u);
+          if (r == SZ_OK) { units.push_back(u); unit_folder.push_back(i); unit_sub.push_back(ci); }
+        }
+      }
+      if (r == SZ_OK && (b.rc_off + b.rc_size > size)) r = SZ_ERROR_INPUT_EOF;
+      if (r == SZ_OK && f.unpack_size > 0xFFFFFFFFull) r = SZ_ERROR_UNSUPPORTED;
+      if (r != SZ_OK)
+      {
+        units.resize(units_before); unit_folder.resize(units_before); unit_sub.resize(units_before); copies.resize(copies_before);
+        folder_res[i] = r;
+        continue;
+      }
+      LzbBcj2Job j;
+      memset(&j, 0, sizeof j);
+      j.main_off = where[2]; j.main_size = (uint32_t)b.sub[2].unpack_size;
+      j.call_off = where[1]; j.call_size = (uint32_t)b.sub[1].unpack_size;
+      j.jump_off = where[0]; j.jump_size = (uint32_t)b.sub[0].unpack_size;
+      j.rc_off = b.rc_off; j.rc_size = (uint32_t)b.rc_size;
+      j.out_off = f.out_off; j.out_size = (uint32_t)f.unpack_size;
+      jobs.push_back(j); job_folder.push_back(i);
+      if (f.crc_defined)
+      {
+        LzbUnit p;
+        memset(&p, 0, sizeof p);
+        p.dst_off = f.out_off; p.dst_cap = (uint32_t)f.unpack_size;
+        p.check = LZB_CHECK_CRC32; p.flags |= LZB_UNIT_VERIFY; p.expect = f.crc;
+        post_a.push_back(p); a_folder.push_back(i);
+      }
+      continue;
+    }
     if (f.method == 0)
     {
       if (f.pack_size != f.unpack_size) { folder_res[i] = SZ_ERROR_DATA; continue; }
@@ -427,7 +515,7 @@ static SRes decode_folders(LzbContext *ctx, const LzbSzArchive &a, const Byte *a
       /* BCJ x86 and the folder CRC ride in the decode launch; ARM and stored folders take the folder pass */
       if (f.filter == LZB_FILTER_X86) u.filter = LZB_FILTER_X86;
       if (f.filter != LZB_FILTER_ARM && f.crc_defined) { u.check = LZB_CHECK_CRC32; u.flags |= LZB_UNIT_VERIFY; u.expect = f.crc; }
-      units.push_back(u); unit_folder.push_back(i);
+      units.push_back(u); unit_folder.push_back(i); unit_sub.push_back(-1);
     }
     if (f.method == 0 || f.filter == LZB_FILTER_ARM)
     {
@@ -452,15 +540,26 @@ static SRes decode_folders(LzbContext *ctx, const LzbSzArchive &a, const Byte *a
     post_b.push_back(p); b_file.push_back(k);
   }
   std::vector<LzbResult> res(units.size()), res_a(post_a.size()), res_b(post_b.size());
-  if (!units.empty() || !post_a.empty() || !post_b.empty() || !copies.empty())
+  if (!units.empty() || !post_a.empty() || !post_b.empty() || !copies.empty() || !jobs.empty())
   {
     if (!ctx) ctx = lzb_default_context();
     if (!ctx) return SZ_ERROR_FAIL;
-    const SRes r = lzb_run_stages(ctx, archive, size, out, out_bytes, copies.data(), copies.size(), units.data(), res.data(), units.size(),
+    const SRes r = lzb_run_stages(ctx, archive, size, out, out_bytes, (size_t)scratch, copies.data(), copies.size(),
+                                  units.data(), res.data(), units.size(), jobs.data(), jobs.size(),
                                   post_a.data(), res_a.data(), post_a.size(), post_b.data(), res_b.data(), post_b.size());
     if (r != SZ_OK) return r;
   }
-  for (size_t j = 0; j < units.size(); j++) folder_res[unit_folder[j]] = folder_verdict(a.folders[unit_folder[j]], units[j], res[j]);
+  for (size_t j = 0; j < units.size(); j++)
+  {
+    const size_t fi = unit_folder[j];
+    if (unit_sub[j] < 0) { folder_res[fi] = folder_verdict(a.folders[fi], units[j], res[j]); continue; }
+    /* coders of a BCJ2 chain run in order 0, 1, 2 in the reference: the first failure is the folder's */
+    const SubCoder &sc = a.bcj2[(size_t)a.bcj2_index[fi]].sub[unit_sub[j]];
+    const SRes v = coder_verdict(sc.method, sc.pack_size, units[j], res[j]);
+    if (folder_res[fi] == SZ_OK && v != SZ_OK) folder_res[fi] = v;
+  }
+  for (size_t j = 0; j < jobs.size(); j++)
+    if (folder_res[job_folder[j]] == SZ_OK && jobs[j].res != SZ_OK) folder_res[job_folder[j]] = (SRes)jobs[j].res;
   for (size_t j = 0; j < post_a.size(); j++)
     if (folder_res[a_folder[j]] == SZ_OK && res_a[j].res != SZ_OK) folder_res[a_folder[j]] = res_a[j].res;
   /* SzArEx_Extract, 7zIn.c:1383-1404: folder verdict first, then the file's place in it, then its own CRC */
@@ -597,6 +696,30 @@ static SRes read_header(Cursor &c, LzbSzArchive &a, UInt64 start_after_header)
     o.supported = (uint8_t)classify_folder(f, o);
     o.pack_off = db.data_pos + pack_pos;
     o.pack_size = pack_index < db.pack_sizes.size() ? db.pack_sizes[pack_index] : 0;
+    a.bcj2_index.push_back(-1);
+    if (o.supported == SZ_OK && o.method == 3 && pack_index + 4 <= db.pack_sizes.size())
+    {
+      /* pack streams of the folder, in order: [0] main (coder 2), [1] range coder (raw), [2] call (coder 1),
+       * [3] jump (coder 0) -- 7zDec.c:358-362,408-411 */
+      Bcj2Folder b;
+      UInt64 off[4], at = o.pack_off;
+      for (int k = 0; k < 4; k++) { off[k] = at; at += db.pack_sizes[pack_index + k]; }
+      static const int stream_of[3] = { 3, 2, 0 };
+      for (int ci = 0; ci < 3; ci++)
+      {
+        const Coder &cd = f.coders[(size_t)ci];
+        SubCoder &sc = b.sub[ci];
+        sc.method = cd.method == kMethodCopy ? 0u : (cd.method == kMethodLzma ? 1u : 2u);
+        sc.props_size = (uint8_t)(cd.props.size() > 255 ? 255 : cd.props.size());
+        memcpy(sc.props, cd.props.data(), cd.props.size() < sizeof sc.props ? cd.props.size() : sizeof sc.props);
+        sc.pack_off = off[stream_of[ci]]; sc.pack_size = db.pack_sizes[pack_index + (size_t)stream_of[ci]];
+        sc.unpack_size = f.unpack_sizes[(size_t)ci];
+      }
+      b.rc_off = off[1]; b.rc_size = db.pack_sizes[pack_index + 1];
+      a.bcj2_index.back() = (int)a.bcj2.size();
+      a.bcj2.push_back(b);
+    }
+    else if (o.method == 3 && o.supported == SZ_OK) o.supported = (uint8_t)SZ_ERROR_ARCHIVE;
     for (size_t k = 0; k < f.pack_streams.size() && pack_index + k < db.pack_sizes.size(); k++) pack_pos += db.pack_sizes[pack_index + k];
     pack_index += f.pack_streams.size();
     o.unpack_size = f.unpack_size();

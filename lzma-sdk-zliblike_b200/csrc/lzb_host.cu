@@ -511,9 +511,10 @@ SRes lzb_run_resident(LzbContext *c, const uint8_t *d_packed, uint8_t *d_out, co
 /* One archive, several dependent passes over the same device-resident arenas (7z folder path): upload the
  * packed bytes once, device-to-device copies for stored ranges, the fused decode pass, then up to two
  * filter/check-only passes (folder level, then file level), one download of the output at the end. */
-SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes, size_t devOutBytes,
                     const LzbCopyRange *copies, size_t n_copies,
                     const LzbUnit *units, LzbResult *results, size_t n,
+                    LzbBcj2Job *bcj2, size_t n_bcj2,
                     const LzbUnit *post_a, LzbResult *res_a, size_t n_a,
                     const LzbUnit *post_b, LzbResult *res_b, size_t n_b)
 {
@@ -522,7 +523,9 @@ SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte 
   LzbSlot &s = c->slot[0];
   const ModelBytes model = model_bytes_for(units, n);
   const size_t most = std::max(n, std::max(n_a, n_b));
-  if (!lzb_slot_reserve(c, s, packedBytes + 16, outBytes + 16, most ? most : 1, n ? slab_bytes_for(model) : 0)) return SZ_ERROR_MEM;
+  if (devOutBytes < outBytes) devOutBytes = outBytes;
+  const size_t jobs_at = (packedBytes + 16 + 15) & ~(size_t)15;             /* the BCJ2 job table rides behind the archive */
+  if (!lzb_slot_reserve(c, s, jobs_at + n_bcj2 * sizeof(LzbBcj2Job) + 16, devOutBytes + 16, most ? most : 1, n ? slab_bytes_for(model) : 0)) return SZ_ERROR_MEM;
   bool ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_packed, packed, packedBytes, cudaMemcpyHostToDevice, s.stream), "H2D archive");
   for (size_t i = 0; ok && i < n_copies; i++)
     ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_out + copies[i].dst_off, s.d_packed + copies[i].src_off, copies[i].len,
@@ -534,6 +537,14 @@ SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte 
     int rc = lzb_launch_decode(s.d_packed, s.d_out, s.d_units, s.d_results, (uint32_t)n, s.d_ticket, model.smem, model.gmem, s.d_slab, s.stream);
     if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
     if (!lzb_cuda_ok(cudaMemcpyAsync(results, s.d_results, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results")) return SZ_ERROR_FAIL;
+  }
+  if (n_bcj2)
+  {
+    LzbBcj2Job *d_jobs = reinterpret_cast<LzbBcj2Job *>(s.d_packed + jobs_at);
+    if (!lzb_cuda_ok(cudaMemcpyAsync(d_jobs, bcj2, n_bcj2 * sizeof(LzbBcj2Job), cudaMemcpyHostToDevice, s.stream), "H2D bcj2 jobs")) return SZ_ERROR_FAIL;
+    int rc = lzb_launch_bcj2(s.d_packed, s.d_out, d_jobs, (uint32_t)n_bcj2, s.stream);
+    if (rc != 0) { lzb_set_error("bcj2 launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+    if (!lzb_cuda_ok(cudaMemcpyAsync(bcj2, d_jobs, n_bcj2 * sizeof(LzbBcj2Job), cudaMemcpyDeviceToHost, s.stream), "D2H bcj2 jobs")) return SZ_ERROR_FAIL;
   }
   const LzbUnit *pu[2] = { post_a, post_b };
   LzbResult *pr[2] = { res_a, res_b };
@@ -824,6 +835,33 @@ extern "C" SizeT x86_Convert(Byte *data, SizeT size, UInt32 ip, UInt32 *state, i
   if (!gpu_filter(data, size, LZB_FILTER_X86, ip, flags, (uint64_t)(*state & 7) << 32, &r)) return 0;
   *state = (UInt32)r.status;
   return r.src_used;
+}
+
+/* ------------------------------------------------------------------ LZMA + x86 one-call form -------- */
+/* reference Lzma86Dec.c:13-56: 1 filter byte, 5 props bytes, 8 size bytes, then a raw LZMA stream */
+extern "C" SRes Lzma86_GetUnpackSize(const Byte *src, SizeT srcLen, UInt64 *unpackSize)
+{
+  if (srcLen < LZMA86_HEADER_SIZE) return SZ_ERROR_INPUT_EOF;
+  *unpackSize = lzb_le64(src + LZMA86_SIZE_OFFSET);
+  return SZ_OK;
+}
+
+extern "C" SRes Lzma86_Decode(Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen)
+{
+  if (*srcLen < LZMA86_HEADER_SIZE) return SZ_ERROR_INPUT_EOF;
+  const int use_filter = src[0];
+  if (use_filter > 1) { *destLen = 0; return SZ_ERROR_UNSUPPORTED; }
+  SizeT pure = *srcLen - LZMA86_HEADER_SIZE;
+  ELzmaStatus status;
+  const SRes res = LzmaDecode(dest, destLen, src + LZMA86_HEADER_SIZE, &pure, src + 1, LZMA_PROPS_SIZE, LZMA_FINISH_ANY, &status, nullptr);
+  *srcLen = pure + LZMA86_HEADER_SIZE;
+  if (res != SZ_OK) return res;
+  if (use_filter == 1)
+  {
+    UInt32 st = 0;
+    x86_Convert(dest, *destLen, 0, &st, 0);
+  }
+  return SZ_OK;
 }
 
 /* reference Bra.c:6-133, BraIA64.c:16-69: stateless, one aligned instruction slot per GPU thread */

@@ -52,9 +52,12 @@ SRes lzb_decode_host_simple(LzbContext *c, const Byte *packed, size_t packedByte
                             const LzbUnit *units, LzbResult *results, size_t n);
 
 struct LzbCopyRange { uint64_t src_off, dst_off, len; };
-SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+/* devOutBytes >= outBytes: size of the device output arena (scratch streams may live behind the part that is
+ * downloaded); bcj2: merges that run between the decode pass and the folder pass */
+SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes, size_t devOutBytes,
                     const LzbCopyRange *copies, size_t n_copies,
                     const LzbUnit *units, LzbResult *results, size_t n,
+                    LzbBcj2Job *bcj2, size_t n_bcj2,
                     const LzbUnit *post_a, LzbResult *res_a, size_t n_a,
                     const LzbUnit *post_b, LzbResult *res_b, size_t n_b);
 

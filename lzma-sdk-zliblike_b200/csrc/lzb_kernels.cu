@@ -186,6 +186,84 @@ lzb_post_only_kernel(uint8_t *__restrict__ data, const LzbUnit *__restrict__ uni
   if (lane == 0) results[i] = r;
 }
 
+/* BCJ2 (Bcj2.c:28-127): x86 branch targets were moved to two side streams (CALL: E8; JUMP: E9 and 0F 8x), one
+ * adaptive bit per candidate (its own little range coder: 256 contexts for E8 by the previous byte, one for E9,
+ * one for Jcc) says whether a candidate was moved.  The merge is one serial chain over the whole folder -- one
+ * thread per folder; the folders of an archive are independent jobs. */
+__global__ void __launch_bounds__(32)
+lzb_bcj2_kernel(const uint8_t *__restrict__ packed, uint8_t *out_arena, LzbBcj2Job *jobs, uint32_t n_jobs)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_jobs) return;
+  LzbBcj2Job job = jobs[j];
+  const uint8_t *main_s = out_arena + job.main_off, *call_s = out_arena + job.call_off, *jump_s = out_arena + job.jump_off;
+  const uint8_t *rc = packed + job.rc_off;
+  uint8_t *out = out_arena + job.out_off;
+  uint16_t p[258];
+  for (int i = 0; i < 258; i++) p[i] = 1024;
+  uint32_t rc_pos = 0, range = 0xFFFFFFFFu, code = 0;
+  int res = LZB_SZ_OK;
+  for (int i = 0; i < 5; i++)
+  {
+    if (rc_pos == job.rc_size) { res = LZB_SZ_ERROR_DATA; break; }
+    code = (code << 8) | rc[rc_pos++];
+  }
+  uint32_t in_pos = 0, out_pos = 0, call_pos = 0, jump_pos = 0;
+  uint8_t prev = 0;
+  if (res == LZB_SZ_OK && job.out_size != 0)
+  {
+    for (;;)
+    {
+      /* plain bytes up to and including the next branch opcode */
+      uint32_t limit = job.main_size - in_pos;
+      if (job.out_size - out_pos < limit) limit = job.out_size - out_pos;
+      while (limit != 0)
+      {
+        const uint8_t b = main_s[in_pos];
+        out[out_pos++] = b;
+        if ((b & 0xFE) == 0xE8 || (prev == 0x0F && (b & 0xF0) == 0x80)) break;
+        in_pos++;
+        prev = b;
+        limit--;
+      }
+      if (limit == 0 || out_pos == job.out_size) break;
+      const uint8_t b = main_s[in_pos++];
+      uint16_t *pr = b == 0xE8 ? p + prev : (b == 0xE9 ? p + 256 : p + 257);
+      const uint32_t t = *pr, bound = (range >> 11) * t;
+      bool moved;
+      if (code < bound) { range = bound; *pr = (uint16_t)(t + ((2048 - t) >> 5)); moved = false; }
+      else { range -= bound; code -= bound; *pr = (uint16_t)(t - (t >> 5)); moved = true; }
+      if (range < (1u << 24))
+      {
+        if (rc_pos == job.rc_size) { res = LZB_SZ_ERROR_DATA; break; }
+        range <<= 8; code = (code << 8) | rc[rc_pos++];
+      }
+      if (!moved) { prev = b; continue; }
+      const uint8_t *v;
+      if (b == 0xE8)
+      {
+        if (job.call_size - call_pos < 4) { res = LZB_SZ_ERROR_DATA; break; }
+        v = call_s + call_pos; call_pos += 4;
+      }
+      else
+      {
+        if (job.jump_size - jump_pos < 4) { res = LZB_SZ_ERROR_DATA; break; }
+        v = jump_s + jump_pos; jump_pos += 4;
+      }
+      const uint32_t dest = (((uint32_t)v[0] << 24) | ((uint32_t)v[1] << 16) | ((uint32_t)v[2] << 8) | v[3]) - (out_pos + 4);
+      out[out_pos++] = (uint8_t)dest;
+      if (out_pos == job.out_size) break;
+      out[out_pos++] = (uint8_t)(dest >> 8);
+      if (out_pos == job.out_size) break;
+      out[out_pos++] = (uint8_t)(dest >> 16);
+      if (out_pos == job.out_size) break;
+      out[out_pos++] = prev = (uint8_t)(dest >> 24);
+    }
+    if (res == LZB_SZ_OK && out_pos != job.out_size) res = LZB_SZ_ERROR_DATA;
+  }
+  jobs[j].res = res;
+}
+
 /* xz block check 10 (SHA-256, Xz.c:45-88): a digest is one serial chain, so one thread per job; blocks of
  * an xz file are independent jobs.  Not fused into the decode kernel: it would grow the hot kernel's code
  * and registers for a check the reference's own encoder never selects by default. */
@@ -364,5 +442,12 @@ extern "C" int lzb_launch_sha256(const uint8_t *d_data, LzbShaJob *d_jobs, uint3
 {
   if (n_jobs == 0) return 0;
   lzb::lzb_sha256_kernel<<<(n_jobs + 31) / 32, 32, 0, stream>>>(d_data, d_jobs, n_jobs);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int lzb_launch_bcj2(const uint8_t *d_packed, uint8_t *d_out, LzbBcj2Job *d_jobs, uint32_t n_jobs, cudaStream_t stream)
+{
+  if (n_jobs == 0) return 0;
+  lzb::lzb_bcj2_kernel<<<(n_jobs + 31) / 32, 32, 0, stream>>>(d_packed, d_out, d_jobs, n_jobs);
   return (int)cudaGetLastError();
 }

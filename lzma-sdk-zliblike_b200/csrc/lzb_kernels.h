@@ -58,6 +58,9 @@ int lzb_launch_decode_flow(const uint8_t *d_packed, uint8_t *d_out, const LzbUni
 int lzb_launch_post_only(uint8_t *d_data, const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units,
                          cudaStream_t stream);
 
+/* BCJ2 merges over streams in device memory, one thread per job (jobs: device array, res written back). */
+int lzb_launch_bcj2(const uint8_t *d_packed, uint8_t *d_out, LzbBcj2Job *d_jobs, uint32_t n_jobs, cudaStream_t stream);
+
 /* SHA-256 over bytes in device memory, one thread per job (jobs: device array, updated in place). */
 int lzb_launch_sha256(const uint8_t *d_data, LzbShaJob *d_jobs, uint32_t n_jobs, cudaStream_t stream);
 

@@ -126,6 +126,18 @@ typedef struct LzbShaJob
   uint8_t digest[32];
 } LzbShaJob;
 
+/* One BCJ2 merge (reference Bcj2.c:28-127; 7z folders with the four-coder x86 chain, 7zDec.c:308-329,406-430):
+ * main / call / jump streams (already decoded, in the output arena) + the raw range-coder stream (in the
+ * packed arena) -> `out_size` bytes at out_off.  The main stream sits at the END of the output range and the
+ * merge runs in place, front to back, exactly as the reference lays it out. */
+typedef struct LzbBcj2Job
+{
+  uint64_t main_off, call_off, jump_off, out_off;   /* offsets in the output arena */
+  uint64_t rc_off;                                  /* offset in the packed arena  */
+  uint32_t main_size, call_size, jump_size, rc_size, out_size;
+  int32_t res;                                      /* SZ_OK / SZ_ERROR_DATA       */
+} LzbBcj2Job;
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,7 @@ what the reference's SzArEx_Open and SzArEx_Extract answer -- for the database (
 map), for every file's bytes, and for the result codes of damaged archives.
 
 Golden: tests/golden/sz.json (tools/make_golden_7z.py): archives written by tools/sz_writer.py from payloads
-the reference's encoders made (Copy / LZMA / LZMA2, BCJ x86, ARM, Delta-as-unsupported, packed header, many
+the reference's encoders made (Copy / LZMA / LZMA2, BCJ x86, ARM, BCJ2 chains, Delta-as-unsupported, packed header, many
 small folders from low entropy to random, empty files and directories), pristine and with 29 mutations each.
 
 CPU part : vectors vs the live reference (needref); the writer's own listing; the public structs.
@@ -50,7 +50,7 @@ def test_golden_is_meaningful():
     assert {c["open_res"] for c in cases} >= {0, 3, 4, 6, 16, 17}
     assert {f["res"] for c in cases for f in c["files"]} >= {0, 1, 3, 4}
     whole = [c for c in cases if c["mut"] is None]
-    assert len(whole) == 5 and sum(c["num_folders"] for c in whole) > 70
+    assert len(whole) == 6 and sum(c["num_folders"] for c in whole) > 70
     assert any(f["is_dir"] for c in whole for f in c["files"]) and any(not f["has_stream"] and not f["is_dir"] for c in whole for f in c["files"])
 
 
@@ -60,7 +60,7 @@ def test_public_structs_have_the_documented_size():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("blob", ["a_plain", "a_packed_header", "b_many", "c_delta_unsupported", "d_empty_only"])
+@pytest.mark.parametrize("blob", ["a_plain", "a_packed_header", "b_many", "c_delta_unsupported", "d_empty_only", "e_bcj2"])
 def test_product_matches_golden(blob):
     import lzb200
     cases, blobs = golden()

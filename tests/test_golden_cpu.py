@@ -100,3 +100,20 @@ def test_kernel_logic_fused_filter_and_check(emu, ora):
     units["expect"][1] ^= 1
     res = emubind.decode_units(np.concatenate((xz, np.zeros(16, np.uint8))), out, units)
     assert res["res"].tolist() == [0, R.SZ_ERROR_CRC] + [0] * (len(units) - 2)
+
+
+@pytest.mark.needref
+def test_lzma86_golden_equals_live_reference(ref):
+    import ctypes as C
+    import json
+    import os
+    from oracle import refbind
+    from tools.make_golden_lzma86 import bind, decode, mutate
+    here = os.path.dirname(os.path.abspath(__file__))
+    cs = json.load(open(os.path.join(here, "golden", "lzma86.json")))["cases"]
+    z = np.load(os.path.join(here, "golden", "lzma86.npz"))
+    L = bind(C.CDLL(refbind.REF_SO))
+    for c in cs:
+        m = tuple(c["mut"]) if c["mut"] else None
+        got = decode(L, mutate(z[c["blob"]].tobytes(), m), c["cap"])
+        assert got == {k: c[k] for k in got}, (c["blob"], c["mut"])

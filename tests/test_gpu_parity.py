@@ -247,3 +247,22 @@ def test_filters_and_checks_large(gpu, ora):
     first, st = lzb200.sdk.delta_decode(data[:40001], 5)
     second, _ = lzb200.sdk.delta_decode(data[40001:100000], 5, st)
     assert np.array_equal(np.concatenate((first, second)), one)
+
+
+def test_golden_lzma86_one_call(gpu):
+    """Lzma86_Decode / Lzma86_GetUnpackSize (Lzma86Dec.c) vs the reference's answers: tests/golden/lzma86.json."""
+    import json
+    import os
+    from tools.make_golden_lzma86 import bind, decode, mutate
+    here = os.path.dirname(os.path.abspath(__file__))
+    cs = json.load(open(os.path.join(here, "golden", "lzma86.json")))["cases"]
+    z = np.load(os.path.join(here, "golden", "lzma86.npz"))
+    L = bind(lzb200.lib.load())
+    assert len(cs) > 60
+    for c in cs:
+        m = tuple(c["mut"]) if c["mut"] else None
+        got = decode(L, mutate(z[c["blob"]].tobytes(), m), c["cap"])
+        want = {k: c[k] for k in got}
+        assert got == want, (c["blob"], c["mut"], c["cap"], got, want)
+        if c["mut"] is None and c["res"] == 0 and c["dest_len"] == c["size"]:
+            assert c["out_crc"] == c["plain_crc"]

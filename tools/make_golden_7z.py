@@ -47,6 +47,13 @@ def archives(ref):
     # c: what the reference refuses: Delta as second coder
     fc = [W.Folder("lzma", [("ok.bin", c[200000:205000].tobytes())]), W.Folder("lzma", [("delta.bin", c[210000:215000].tobytes())], filt="delta")]
     out["c_delta_unsupported"] = (W.write_archive(ref, fc), fc, [], [])
+    # e: BCJ2 folders (what 7-Zip writes for x86 executables): three LZMA streams + the four-stream merge
+    code2 = add_x86_callsites(c[300000:420000], seed=14).tobytes()
+    fe = [W.Folder("lzma", [("readme.txt", c[430000:436000].tobytes())]),
+          W.Folder("lzma", [("prog.exe", code2[:70000]), ("lib.dll", code2[70000:])], filt="bcj2"),
+          W.Folder("lzma", [("tiny.exe", bytes([0x90, 0xE8, 1, 2, 3, 4, 0xC3, 0xE9]))], filt="bcj2"),
+          W.Folder("lzma2", [("tail.bin", c[440000:450000].tobytes())])]
+    out["e_bcj2"] = (W.write_archive(ref, fe, encode_header=True), fe, [], [])
     # d: only empty entries
     out["d_empty_only"] = (W.write_archive(ref, [], empty_files=["e1", "e2"], dirs=["d1"]), [], ["e1", "e2"], ["d1"])
     return out

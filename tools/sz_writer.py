@@ -19,7 +19,7 @@ K_END, K_HEADER, K_MAIN_STREAMS, K_FILES, K_PACK, K_UNPACK, K_SUBSTREAMS, K_SIZE
 K_CODERS_UNPACK, K_NUM_UNPACK, K_EMPTY_STREAM, K_EMPTY_FILE, K_NAME, K_MTIME, K_ATTR, K_ENCODED = 12, 13, 14, 15, 17, 20, 21, 23
 SIG = b"7z\xBC\xAF\x27\x1C"
 M_COPY, M_LZMA, M_LZMA2 = b"\x00", b"\x03\x01\x01", b"\x21"
-M_BCJ, M_ARM, M_DELTA = b"\x03\x03\x01\x03", b"\x03\x03\x05\x01", b"\x03"
+M_BCJ, M_ARM, M_DELTA, M_BCJ2 = b"\x03\x03\x01\x03", b"\x03\x03\x05\x01", b"\x03", b"\x03\x03\x01\x1B"
 
 
 def num(v: int) -> bytes:
@@ -57,6 +57,11 @@ class Folder:
     packed: bytes = b""
     props: bytes = b""
     plain: bytes = b""
+    # filt == "bcj2": the four pack streams [main, range coder, call, jump], the props of the three LZMA coders
+    # [jump, call, main] (coder order) and the sizes of their outputs
+    pack_list: list = field(default_factory=list)
+    sub_props: list = field(default_factory=list)
+    sub_sizes: list = field(default_factory=list)
 
 
 def _filter(ref, data: bytes, filt):
@@ -71,9 +76,91 @@ def _filter(ref, data: bytes, filt):
     return data
 
 
+class _RangeEnc:
+    """LZMA-style binary range encoder (the inverse of the decoder in Bcj2.c:9-21)."""
+    def __init__(self):
+        self.low, self.range, self.cache, self.cache_size, self.out = 0, 0xFFFFFFFF, 0, 1, bytearray()
+
+    def _shift(self):
+        if self.low < 0xFF000000 or self.low >= (1 << 32):
+            carry = self.low >> 32
+            temp = self.cache
+            while True:
+                self.out.append((temp + carry) & 0xFF)
+                temp = 0xFF
+                self.cache_size -= 1
+                if self.cache_size == 0:
+                    break
+            self.cache = (self.low >> 24) & 0xFF
+        self.cache_size += 1
+        self.low = (self.low & 0x00FFFFFF) << 8
+
+    def bit(self, probs, i, b):
+        p = probs[i]
+        bound = (self.range >> 11) * p
+        if b == 0:
+            self.range = bound
+            probs[i] = p + ((2048 - p) >> 5)
+        else:
+            self.low += bound
+            self.range -= bound
+            probs[i] = p - (p >> 5)
+        while self.range < (1 << 24):
+            self.range = (self.range << 8) & 0xFFFFFFFF
+            self._shift()
+
+    def finish(self):
+        for _ in range(5):
+            self._shift()
+        return bytes(self.out)
+
+
+def bcj2_encode(data: bytes, every: int = 3):
+    """Split x86 code into (main, call, jump, rc) as the decoder of Bcj2.c:28-127 expects them.  Which branch
+    targets are moved is the encoder's choice; here: all whose four operand bytes exist, except every `every`-th
+    candidate (so that both decisions and the in-operand rescans are exercised)."""
+    n = len(data)
+    main, call, jump = bytearray(), bytearray(), bytearray()
+    rc, probs = _RangeEnc(), [1024] * 258
+    prev, i, k = 0, 0, 0
+    while i < n:
+        b = data[i]
+        main.append(b)
+        is_j = (b & 0xFE) == 0xE8 or (prev == 0x0F and (b & 0xF0) == 0x80)
+        i += 1
+        if not is_j:
+            prev = b
+            continue
+        if i == n:                      # the opcode is the last byte: the decoder stops before asking for a bit
+            break
+        ctx = prev if b == 0xE8 else (256 if b == 0xE9 else 257)
+        k += 1
+        if i + 4 <= n and k % every != 0:
+            rc.bit(probs, ctx, 1)
+            rel = int.from_bytes(data[i:i + 4], "little")
+            dest = (rel + i + 4) & 0xFFFFFFFF
+            (call if b == 0xE8 else jump).extend(dest.to_bytes(4, "big"))
+            prev = data[i + 3]
+            i += 4
+        else:
+            rc.bit(probs, ctx, 0)
+            prev = b
+    return bytes(main), bytes(call), bytes(jump), rc.finish()
+
+
 def encode_folder(ref, f: Folder):
     import numpy as np
     f.plain = b"".join(d for _, d in f.files)
+    if f.filt == "bcj2":
+        main, call, jump, rcs = bcj2_encode(f.plain)
+        packs, props = [], []
+        for part in (jump, call, main):                  # coder order 0, 1, 2
+            pk, pr = ref.lzma_encode(np.frombuffer(part, dtype=np.uint8) if part else np.zeros(0, np.uint8), level=f.level, dict_size=f.dict_size)
+            packs.append(pk.tobytes()); props.append(pr.tobytes())
+        f.pack_list = [packs[2], rcs, packs[1], packs[0]]  # pack stream order: main, range coder, call, jump
+        f.sub_props, f.sub_sizes = props, [len(jump), len(call), len(main)]
+        f.packed = b"".join(f.pack_list)
+        return f
     pre = _filter(ref, f.plain, f.filt)
     if f.method == "copy":
         f.packed, f.props = pre, b""
@@ -92,6 +179,18 @@ def _coder(method: bytes, props: bytes = b"") -> bytes:
 
 
 def _folder_record(f: Folder) -> bytes:
+    if f.filt == "bcj2":
+        # three LZMA coders (in 0,1,2 / out 0,1,2), then BCJ2 with four inputs (in 3..6) and one output (out 3);
+        # its inputs 3,4,5 are fed by outputs 2,1,0; pack streams feed inputs 2, 6, 1, 0 (7zDec.c:308-329)
+        rec = num(4)
+        for pr in f.sub_props:
+            rec += _coder(M_LZMA, pr)
+        rec += bytes([len(M_BCJ2) | 0x10]) + M_BCJ2 + num(4) + num(1)
+        for a, b in ((5, 0), (4, 1), (3, 2)):
+            rec += num(a) + num(b)
+        for ps in (2, 6, 1, 0):
+            rec += num(ps)
+        return rec
     main = {"copy": M_COPY, "lzma": M_LZMA, "lzma2": M_LZMA2}[f.method]
     if f.filt is None:
         return num(1) + _coder(main, f.props)
@@ -103,15 +202,21 @@ def _folder_record(f: Folder) -> bytes:
 
 def _streams_info(folders, data_offset: int, sub=True) -> bytes:
     live = [f for f in folders]
-    out = bytearray([K_PACK]) + num(data_offset) + num(len(live)) + bytes([K_SIZE])
-    for f in live:
-        out += num(len(f.packed))
+    streams = [p for f in live for p in (f.pack_list if f.pack_list else [f.packed])]
+    out = bytearray([K_PACK]) + num(data_offset) + num(len(streams)) + bytes([K_SIZE])
+    for p in streams:
+        out += num(len(p))
     out += bytes([K_END])
     out += bytes([K_UNPACK, K_FOLDER]) + num(len(live)) + b"\x00"
     for f in live:
         out += _folder_record(f)
     out += bytes([K_CODERS_UNPACK])
     for f in live:
+        if f.filt == "bcj2":
+            for z in f.sub_sizes:
+                out += num(z)
+            out += num(len(f.plain))
+            continue
         out += num(len(f.plain))
         if f.filt is not None:
             out += num(len(f.plain))

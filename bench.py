@@ -367,7 +367,7 @@ def main():
     # ---------------- e2e: host arenas through the C-ABI, copies inside the timed region
     e2e = None
     if not a.no_e2e:
-        for _ in range(min(a.warmup, 2)):
+        for _ in range(max(a.warmup, 1)):
             lzb200.sdk.decode_units_host(ctx, h_packed, h_out, units)
         sync_all()
         t0 = time.perf_counter()

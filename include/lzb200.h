@@ -174,6 +174,9 @@ SizeT ARMT_Convert(Byte *data, SizeT size, UInt32 ip, int encoding);
 SizeT PPC_Convert(Byte *data, SizeT size, UInt32 ip, int encoding);
 SizeT SPARC_Convert(Byte *data, SizeT size, UInt32 ip, int encoding);
 SizeT IA64_Convert(Byte *data, SizeT size, UInt32 ip, int encoding);
+/* BCJ2 merge (Bcj2.h:24-30): buf0 main, buf1 CALL targets, buf2 JUMP targets, buf3 range-coder stream */
+int Bcj2_Decode(const Byte *buf0, SizeT size0, const Byte *buf1, SizeT size1, const Byte *buf2, SizeT size2,
+                const Byte *buf3, SizeT size3, Byte *outBuf, SizeT outSize);
 #define DELTA_STATE_SIZE 256
 void Delta_Init(Byte *state);
 void Delta_Encode(Byte *state, unsigned delta, Byte *data, SizeT size);

@@ -864,6 +864,44 @@ extern "C" SRes Lzma86_Decode(Byte *dest, SizeT *destLen, const Byte *src, SizeT
   return SZ_OK;
 }
 
+/* ------------------------------------------------------------------ BCJ2 merge, stand-alone ---------- */
+/* reference Bcj2.c:28-127 (Bcj2.h:24-30): the four streams go to the device, one thread merges them */
+extern "C" int Bcj2_Decode(const Byte *buf0, SizeT size0, const Byte *buf1, SizeT size1, const Byte *buf2, SizeT size2,
+                           const Byte *buf3, SizeT size3, Byte *outBuf, SizeT outSize)
+{
+  if ((size0 | size1 | size2 | size3 | outSize) > 0xFFFFFFFFull) { lzb_set_error("Bcj2_Decode: stream larger than 4 GiB"); return SZ_ERROR_UNSUPPORTED; }
+  LzbContext *c = lzb_default_context();
+  if (!c) return SZ_ERROR_FAIL;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
+  LzbSlot &s = c->slot[0];
+  auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  /* output arena: [out | main | call | jump]; packed arena: [range-coder stream | job] */
+  LzbBcj2Job j;
+  memset(&j, 0, sizeof j);
+  j.out_off = 0; j.out_size = (uint32_t)outSize;
+  j.main_off = up16(outSize); j.main_size = (uint32_t)size0;
+  j.call_off = j.main_off + up16(size0); j.call_size = (uint32_t)size1;
+  j.jump_off = j.call_off + up16(size1); j.jump_size = (uint32_t)size2;
+  j.rc_off = 0; j.rc_size = (uint32_t)size3;
+  const size_t job_at = up16(size3 + 16);
+  if (!lzb_slot_reserve(c, s, job_at + sizeof j + 16, (size_t)(j.jump_off + up16(size2)) + 16, 1, 0)) return SZ_ERROR_MEM;
+  LzbBcj2Job *d_job = reinterpret_cast<LzbBcj2Job *>(s.d_packed + job_at);
+  bool ok = true;
+  if (size0) ok = ok && lzb_cuda_ok(cudaMemcpyAsync(s.d_out + j.main_off, buf0, size0, cudaMemcpyHostToDevice, s.stream), "H2D bcj2 main");
+  if (size1) ok = ok && lzb_cuda_ok(cudaMemcpyAsync(s.d_out + j.call_off, buf1, size1, cudaMemcpyHostToDevice, s.stream), "H2D bcj2 call");
+  if (size2) ok = ok && lzb_cuda_ok(cudaMemcpyAsync(s.d_out + j.jump_off, buf2, size2, cudaMemcpyHostToDevice, s.stream), "H2D bcj2 jump");
+  if (size3) ok = ok && lzb_cuda_ok(cudaMemcpyAsync(s.d_packed, buf3, size3, cudaMemcpyHostToDevice, s.stream), "H2D bcj2 rc");
+  ok = ok && lzb_cuda_ok(cudaMemcpyAsync(d_job, &j, sizeof j, cudaMemcpyHostToDevice, s.stream), "H2D bcj2 job");
+  if (!ok) return SZ_ERROR_FAIL;
+  const int rc = lzb_launch_bcj2(s.d_packed, s.d_out, d_job, 1, s.stream);
+  if (rc != 0) { lzb_set_error("bcj2 launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+  if (outSize) ok = ok && lzb_cuda_ok(cudaMemcpyAsync(outBuf, s.d_out, outSize, cudaMemcpyDeviceToHost, s.stream), "D2H bcj2 out");
+  ok = ok && lzb_cuda_ok(cudaMemcpyAsync(&j, d_job, sizeof j, cudaMemcpyDeviceToHost, s.stream), "D2H bcj2 job") &&
+       lzb_cuda_ok(cudaStreamSynchronize(s.stream), "bcj2 kernel");
+  return ok ? j.res : SZ_ERROR_FAIL;
+}
+
 /* reference Bra.c:6-133, BraIA64.c:16-69: stateless, one aligned instruction slot per GPU thread */
 static SizeT risc_convert(int filter, Byte *data, SizeT size, UInt32 ip, int encoding, SizeT min_size)
 {

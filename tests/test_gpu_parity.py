@@ -266,3 +266,31 @@ def test_golden_lzma86_one_call(gpu):
         assert got == want, (c["blob"], c["mut"], c["cap"], got, want)
         if c["mut"] is None and c["res"] == 0 and c["dest_len"] == c["size"]:
             assert c["out_crc"] == c["plain_crc"]
+
+
+@pytest.mark.needref
+def test_bcj2_decode_stand_alone(gpu, ref):
+    """Bcj2_Decode (Bcj2.c:28-127) vs the reference on streams split by the fixture encoder: whole, short output,
+    truncated side streams, corrupted range-coder stream."""
+    import ctypes as C
+    from oracle import refbind
+    from tools import sz_writer as W
+    R = C.CDLL(refbind.REF_SO)
+    P = lzb200.lib.load()
+    for L in (R, P):
+        L.Bcj2_Decode.restype = C.c_int
+        L.Bcj2_Decode.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
+                                  C.c_void_p, C.c_size_t]
+    data = add_x86_callsites(make_corpus(150000, seed=77), seed=3).tobytes()
+    m, c, j, r = W.bcj2_encode(data)
+    variants = [(m, c, j, r, len(data)), (m, c, j, r, len(data) // 2), (m, c, j, r, 0), (m, c[:-4], j, r, len(data)), (m, c, j[:8], r, len(data)),
+                (m, c, j, r[: len(r) // 2], len(data)), (m, c, j, r[:3], len(data)), (m[:-10], c, j, r, len(data)), (m, c, j, bytes([r[0] ^ 0x40]) + r[1:], len(data)),
+                (m, c, j, r[:20] + bytes([r[20] ^ 0x08]) + r[21:], len(data))]
+    for k, (a0, a1, a2, a3, n) in enumerate(variants):
+        o1, o2 = np.zeros(n + 8, np.uint8), np.zeros(n + 8, np.uint8)
+        r1 = R.Bcj2_Decode(a0, len(a0), a1, len(a1), a2, len(a2), a3, len(a3), o1.ctypes.data, n)
+        r2 = P.Bcj2_Decode(a0, len(a0), a1, len(a1), a2, len(a2), a3, len(a3), o2.ctypes.data, n)
+        assert r1 == r2, (k, r1, r2)
+        if r1 == 0:
+            assert np.array_equal(o1[:n], o2[:n]), k
+    assert R.Bcj2_Decode(m, len(m), c, len(c), j, len(j), r, len(r), o1.ctypes.data, len(data)) == 0 and o1[: len(data)].tobytes() == data

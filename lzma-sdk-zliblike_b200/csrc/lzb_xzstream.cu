@@ -90,7 +90,9 @@ static void sha_absorb(CSha256 *p, const Byte *data, size_t size, bool on_gpu)
   memcpy(p->buffer, data, size);
 }
 
-extern "C" void Sha256_Update(CSha256 *p, const Byte *data, size_t size) { sha_absorb(p, data, size, size >= 4096); }
+/* the exported object hashes its whole blocks on the device; only this library's own framing bytes (index
+ * records inside XzUnpacker_Code) take the host routine */
+extern "C" void Sha256_Update(CSha256 *p, const Byte *data, size_t size) { sha_absorb(p, data, size, true); }
 
 extern "C" void Sha256_Final(CSha256 *p, Byte *digest)
 {

@@ -33,15 +33,59 @@ def shape(rng, n):
     return (np.arange(n) * int(rng.integers(1, 7)) // int(rng.integers(1, 9))).astype(np.uint8)
 
 
+def fuzz_lzma2(a, ref, lzb200, ctx):
+    """multi-unit LZMA2 streams (independently encoded units, EOS stripped from all but the last) through
+    Lzma2Decode, which cuts them at the dictionary resets and decodes the units in parallel"""
+    rng = np.random.default_rng(a.seed)
+    total = bad = 0
+    for rd in range(a.rounds):
+        parts, plains = [], []
+        prop = 0
+        nunits = int(rng.integers(1, 7))
+        ds = int(rng.choice([1 << 12, 1 << 16, 1 << 20]))
+        for k in range(nunits):
+            n = int(rng.choice([1, 50, 3000, 70000, 200000, 2200000]))
+            data = shape(rng, n)
+            pk, prop = ref.lzma2_encode(data, level=int(rng.choice([0, 1, 5])), dict_size=ds)
+            parts.append(pk if k == nunits - 1 else pk[:-1])
+            plains.append(data)
+        blob = np.concatenate(parts)
+        total_out = sum(len(p) for p in plains)
+        for variant in range(6):
+            b, cap, fm = blob.copy(), total_out, int(rng.integers(0, 2))
+            if variant == 1:
+                b[int(rng.integers(0, len(b)))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            elif variant == 2:
+                b = b[: int(rng.integers(0, len(b) + 1))]
+            elif variant == 3:
+                cap = int(rng.integers(0, total_out + 10))
+            elif variant == 4:
+                b = b[:-1]
+            g = lzb200.sdk.lzma2_decode(b, prop, cap, fm, ctx)
+            w = ref.lzma2_decode(b, prop, cap, fm)
+            total += 1
+            ok = (g["res"], g["status"], g["dest_len"], g["src_len"]) == (w["res"], w["status"], w["dest_len"], w["src_len"]) and \
+                np.array_equal(g["out"][: g["dest_len"]], w["out"][: w["dest_len"]])
+            if not ok:
+                bad += 1
+                print(f"MISMATCH lzma2 round {rd} variant {variant}: units {nunits} dict {ds} gpu {(g['res'], g['status'], g['dest_len'], g['src_len'])} "
+                      f"ref {(w['res'], w['status'], w['dest_len'], w['src_len'])}", flush=True)
+    print("FUZZ lzma2", "FAILED" if bad else "OK", total, "decodes", bad, "mismatches")
+    return 1 if bad else 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=40)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--lzma2", action="store_true")
     a = ap.parse_args()
     import lzb200
     from oracle import refbind
     ref = refbind.ref()
     ctx = lzb200.lib.Context(0)
+    if a.lzma2:
+        return fuzz_lzma2(a, ref, lzb200, ctx)
     rng = np.random.default_rng(a.seed)
     total = bad = 0
     for rd in range(a.rounds):

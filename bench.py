@@ -17,6 +17,9 @@ far larger than the 126 MB L2, so no step is served from cache).  A step is one 
            per-GPU work is fixed ("weak"); time = max over ranks, value = all ranks' bytes / that time.
   --impl reference : the unmodified reference decoder (oracle/_ref/libref.so, one unit per host thread)
            on a bounded sample of the same batch.
+Extra keys beside the contract's: `issue_roofline` (the bound that actually limits the kernel: issued warp
+instructions per SM and cycle, of 4), `e2e.per_call_ms`, and for --workload xz4m `container_e2e` (the same blocks
+as ONE .xz file through XzDecodeParallel).
 """
 from __future__ import annotations
 
@@ -449,6 +452,15 @@ def main():
                     note="serial range-decoder chain: bound by resident units x issue slots, far below the HBM roof; "
                          "traffic above the algorithmic bytes = match sources evicted from L2 (profiles/r01_c_residency.md)")
 
+    # what actually bounds the kernel: issue slots.  Warp instructions per output byte is a
+    # property of the code + corpus measured by ncu (profiles/r01_f_final.md); the rest is measured live here.
+    issue = None
+    if a.workload == "lzma64k" and clocks.get("sm_mhz"):
+        wi_per_byte = 107.6
+        ipc = wi_per_byte * t["sum_u"] / (kms * 1e-3) / (clocks["sm_mhz"] * 1e6) / float(ctx.sms or 148)
+        issue = dict(bound="issue slots", warp_instr_per_output_byte=wi_per_byte, achieved_ipc_per_sm=ipc, peak_ipc_per_sm=4.0, frac=ipc / 4.0,
+                     source="ncu smsp__inst_executed.sum / output bytes (profiles/r01_f_final.md) x live kernel time and SM clock")
+
     # ---------------- CPU baseline on this box (rank 0, N=1 only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -472,6 +484,8 @@ def main():
                     ratio=dict(packed_over_unpacked=t["sum_p"] / t["sum_u"]))
         if container:
             line["container_e2e"] = container
+        if issue:
+            line["issue_roofline"] = issue
         print(json.dumps(line))
     if dist:
         dist.barrier()

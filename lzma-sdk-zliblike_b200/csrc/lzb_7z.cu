@@ -544,7 +544,17 @@ static SRes decode_folders(LzbContext *ctx, const LzbSzArchive &a, const Byte *a
   {
     if (!ctx) ctx = lzb_default_context();
     if (!ctx) return SZ_ERROR_FAIL;
-    const SRes r = lzb_run_stages(ctx, archive, size, out, out_bytes, (size_t)scratch, copies.data(), copies.size(),
+    /* nothing but decode units (+ fused BCJ / folder CRC) and file checks: the decode pass can be one streamed
+     * launch, with the outputs going down while later folders still decode */
+    bool streamed = false;
+    if (copies.empty() && jobs.empty() && post_a.empty() && !units.empty())
+    {
+      const SRes r = lzb_flow_then_checks(ctx, archive, size, out, out_bytes, units.data(), res.data(), units.size(),
+                                          post_b.data(), res_b.data(), post_b.size(), &streamed);
+      if (r != SZ_OK) return r;
+    }
+    const SRes r = streamed ? SZ_OK :
+                   lzb_run_stages(ctx, archive, size, out, out_bytes, (size_t)scratch, copies.data(), copies.size(),
                                   units.data(), res.data(), units.size(), jobs.data(), jobs.size(),
                                   post_a.data(), res_a.data(), post_a.size(), post_b.data(), res_b.data(), post_b.size());
     if (r != SZ_OK) return r;

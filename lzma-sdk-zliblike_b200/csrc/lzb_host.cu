@@ -375,6 +375,55 @@ static SRes decode_units_flow(LzbContext *c, const Byte *packed, size_t packedBy
   return ret;
 }
 
+/* may this batch take the streamed launch?  (caller holds the context lock) */
+static bool flow_eligible(LzbContext *c, const Byte *packed, size_t packedBytes, const Byte *out, size_t outBytes,
+                          const LzbUnit *units, size_t n, uint64_t total_out)
+{
+  size_t free_b = 0, total_b = 0;
+  const char *mode = getenv("LZB_FLOW");
+  const bool want = !c->flow_off && (mode ? atoi(mode) != 0 : total_out >= (256ull << 20));
+  /* page-locked arenas only: copies from pageable memory block the calling thread, which must stay free to
+   * feed and drain the launch */
+  auto pinned = [](const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  if (!(want && n != 0 && n < 0xFFFFFFFFull && pinned(packed) && pinned(out) && flow_layout_ok(units, n) &&
+        cudaMemGetInfo(&free_b, &total_b) == cudaSuccess))
+    return false;
+  const LzbSlot &s0 = c->slot[0];
+  const uint64_t have = (uint64_t)free_b + s0.packed_cap + s0.out_cap;
+  return (uint64_t)packedBytes + outBytes + (1ull << 30) < have;
+}
+
+/* 7z: the decode pass as a streamed launch (outputs go down while later folders still decode), then a
+ * check-only pass over the output that is still resident.  *used = false: not eligible, nothing was done. */
+SRes lzb_flow_then_checks(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+                          const LzbUnit *units, LzbResult *results, size_t n,
+                          const LzbUnit *checks, LzbResult *check_results, size_t n_checks, bool *used)
+{
+  *used = false;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
+  uint64_t total_out = 0;
+  for (size_t i = 0; i < n; i++) total_out += units[i].dst_cap;
+  if (!flow_eligible(c, packed, packedBytes, out, outBytes, units, n, total_out)) return SZ_OK;
+  const ModelBytes model = model_bytes_for(units, n);
+  const SRes r = decode_units_flow(c, packed, packedBytes, out, outBytes, units, results, n, model, slab_bytes_for(model), total_out);
+  if (r == LZB_FLOW_STALLED) { c->flow_off = true; return SZ_OK; }
+  *used = true;
+  if (r != SZ_OK || n_checks == 0) return r;
+  LzbSlot &s = c->slot[0];
+  if (!lzb_slot_reserve(c, s, 0, 0, std::max(n, n_checks), 0)) return SZ_ERROR_MEM;
+  if (!lzb_cuda_ok(cudaMemcpyAsync(s.d_units, checks, n_checks * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D check units")) return SZ_ERROR_FAIL;
+  const int rc = lzb_launch_post_only(s.d_out, s.d_units, s.d_results, (uint32_t)n_checks, s.stream);
+  if (rc != 0) { lzb_set_error("post launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+  if (!lzb_cuda_ok(cudaMemcpyAsync(check_results, s.d_results, n_checks * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H check results") ||
+      !lzb_cuda_ok(cudaStreamSynchronize(s.stream), "check pass")) return SZ_ERROR_FAIL;
+  return SZ_OK;
+}
+
 extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
                                     const LzbUnit *units, LzbResult *results, size_t n)
 {
@@ -393,29 +442,11 @@ extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t pa
   const ModelBytes model = model_bytes_for(units, n);
   const size_t slab = slab_bytes_for(model);
   /* big batches whose arenas fit in device memory next to each other: one streamed launch */
+  if (flow_eligible(c, packed, packedBytes, out, outBytes, units, n, total_out))
   {
-    size_t free_b = 0, total_b = 0;
-    const char *mode = getenv("LZB_FLOW");
-    const bool want = !c->flow_off && (mode ? atoi(mode) != 0 : total_out >= (256ull << 20));
-    /* page-locked arenas only: copies from pageable memory block the calling thread, which must stay free to
-     * feed and drain the launch */
-    auto pinned = [](const void *p) {
-      cudaPointerAttributes a;
-      if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-      return a.type == cudaMemoryTypeHost;
-    };
-    if (want && n < 0xFFFFFFFFull && pinned(packed) && pinned(out) && flow_layout_ok(units, n) &&
-        cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
-    {
-      const LzbSlot &s0 = c->slot[0];
-      const uint64_t have = (uint64_t)free_b + s0.packed_cap + s0.out_cap;
-      if ((uint64_t)packedBytes + outBytes + (1ull << 30) < have)
-      {
-        const SRes r = decode_units_flow(c, packed, packedBytes, out, outBytes, units, results, n, model, slab, total_out);
-        if (r != LZB_FLOW_STALLED) return r;
-        c->flow_off = true;                              /* sticky: sliced launches from here on */
-      }
-    }
+    const SRes r = decode_units_flow(c, packed, packedBytes, out, outBytes, units, results, n, model, slab, total_out);
+    if (r != LZB_FLOW_STALLED) return r;
+    c->flow_off = true;                                  /* sticky: sliced launches from here on */
   }
   std::vector<Slice> slices;
   {

@@ -61,6 +61,10 @@ SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte 
                     const LzbUnit *post_a, LzbResult *res_a, size_t n_a,
                     const LzbUnit *post_b, LzbResult *res_b, size_t n_b);
 
+SRes lzb_flow_then_checks(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+                          const LzbUnit *units, LzbResult *results, size_t n,
+                          const LzbUnit *checks, LzbResult *check_results, size_t n_checks, bool *used);
+
 SRes lzb_run_resident(LzbContext *c, const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *units, LzbResult *results, size_t n);
 
 /* little helpers */

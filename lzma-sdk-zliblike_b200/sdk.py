@@ -233,10 +233,15 @@ SZ_FILE_DTYPE = np.dtype([("size", "<u8"), ("out_off", "<u8"), ("folder", "<u4")
 assert SZ_FOLDER_DTYPE.itemsize == 64 and SZ_FILE_DTYPE.itemsize == 56
 
 
-def sz_extract_all(archive, ctx=None) -> dict:
-    """SzArchive_Open + SzArchive_ExtractAll: the reference's SzArEx_Open / SzArEx_Extract for every file."""
+def sz_extract_all(archive, ctx=None, pinned: bool = False) -> dict:
+    """SzArchive_Open + SzArchive_ExtractAll: the reference's SzArEx_Open / SzArEx_Extract for every file.
+    pinned: stage archive and output in page-locked memory (what lets the decode pass be a streamed launch)."""
     L = _lib.load()
     arc = _u8(archive)
+    if pinned:
+        pa = pinned_empty(max(len(arc), 1))
+        pa[: len(arc)] = arc
+        arc = pa[: len(arc)]
     L.SzArchive_Open.restype = C.c_int
     L.SzArchive_Open.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     L.SzArchive_Free.argtypes = [C.c_void_p]
@@ -266,7 +271,7 @@ def sz_extract_all(archive, ctx=None) -> dict:
         pn = L.SzArchive_Names(h, C.byref(nn))
         names = np.ctypeslib.as_array(C.cast(pn, C.POINTER(C.c_uint16)), shape=(nn.value,)).copy() if nn.value else np.zeros(0, np.uint16)
         total = int(L.SzArchive_UnpackSize(h))
-        out = np.zeros(total + 16, np.uint8)
+        out = pinned_empty(total + 16) if pinned else np.zeros(total + 16, np.uint8)
         fres, ires = np.zeros(max(nfo, 1), np.int32), np.zeros(max(nfi, 1), np.int32)
         r2 = L.SzArchive_ExtractAll(ctx.h if ctx else None, h, _p(arc), len(arc), _p(out), total, _p(fres), _p(ires))
         if r2 == R.SZ_ERROR_FAIL:

@@ -88,7 +88,24 @@ def test_all_folders_in_one_pass_and_bytes_match_the_writer():
         data = np.where(rng.random(n) < i / 199.0, rng.integers(0, 256, n), (np.arange(n) // 5) % 11).astype(np.uint8).tobytes()
         folders.append(W.Folder("lzma2" if i & 1 else "lzma", [(f"n{i}.bin", data)], filt="bcj" if i % 7 == 0 else None, dict_size=1 << 15))
     arc = W.write_archive(ref, folders, encode_header=True)
-    d = lzb200.sdk.sz_extract_all(arc)
-    assert d["open_res"] == 0 and d["num_folders"] == 200 and all(r == 0 for r in d["folder_res"])
-    for f, (nm, data) in zip(d["files"], W.expected_listing(folders)):
-        assert f["res"] == 0 and f["name"] == nm and d["out"][f["off"]:f["off"] + f["size"]].tobytes() == data
+    import os
+    # pageable buffers (staged passes), then page-locked ones with the streamed decode pass forced on
+    for pinned in (False, True):
+        os.environ["LZB_FLOW"] = "1"
+        try:
+            d = lzb200.sdk.sz_extract_all(arc, pinned=pinned)
+        finally:
+            os.environ.pop("LZB_FLOW", None)
+        assert d["open_res"] == 0 and d["num_folders"] == 200 and all(r == 0 for r in d["folder_res"])
+        for f, (nm, data) in zip(d["files"], W.expected_listing(folders)):
+            assert f["res"] == 0 and f["name"] == nm and d["out"][f["off"]:f["off"] + f["size"]].tobytes() == data
+    # a damaged member must still be found by the check pass that follows the streamed launch
+    bad = bytearray(arc)
+    bad[len(arc) // 2] ^= 0x20
+    os.environ["LZB_FLOW"] = "1"
+    try:
+        a, b = lzb200.sdk.sz_extract_all(bytes(bad), pinned=False), lzb200.sdk.sz_extract_all(bytes(bad), pinned=True)
+    finally:
+        os.environ.pop("LZB_FLOW", None)
+    assert a["open_res"] == b["open_res"] and [f["res"] for f in a["files"]] == [f["res"] for f in b["files"]]
+    assert a["open_res"] != 0 or any(f["res"] != 0 for f in a["files"])

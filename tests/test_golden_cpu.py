@@ -117,3 +117,30 @@ def test_lzma86_golden_equals_live_reference(ref):
         m = tuple(c["mut"]) if c["mut"] else None
         got = decode(L, mutate(z[c["blob"]].tobytes(), m), c["cap"])
         assert got == {k: c[k] for k in got}, (c["blob"], c["mut"])
+
+
+def test_second_opinion_liblzma_agrees_with_the_oracle(ora):
+    """liblzma (python `lzma`) as an independent decoder of the golden raw-LZMA streams
+    (.lzma framing: 5 props bytes + 8 size bytes + stream) and of the golden xz containers."""
+    import lzma
+    blobs, _ = cases.golden()
+    n = 0
+    for c in cases.cases_of("lzma"):
+        if c["mut"] is not None or c["res"] != 0 or c["dest_len"] != c["cap"] or c["cap"] == 0 or c["finish"] != 0:
+            continue
+        if c["src_len"] != len(blobs[c["blob"]]):
+            continue                                        # an end mark follows: .lzma with a known size does not allow one
+        props = bytes.fromhex(c["props"])
+        if props[0] // 9 // 5 > 4 or (props[0] % 9) + (props[0] // 9) % 5 > 4:
+            continue                                        # liblzma refuses lc + lp > 4
+        alone = props + int(c["cap"]).to_bytes(8, "little") + blobs[c["blob"]].tobytes()
+        want = lzma.LZMADecompressor(format=lzma.FORMAT_ALONE).decompress(alone, max_length=c["cap"])
+        got = ora.lzma_decode(blobs[c["blob"]], props, c["cap"], 0)
+        assert got["res"] == 0 and got["out"][: got["dest_len"]].tobytes() == want, c["blob"]
+        n += 1
+    assert n >= 5
+    for c in cases.cases_of("xz"):
+        if c["mut"] is None:
+            want = lzma.decompress(blobs[c["blob"]].tobytes(), format=lzma.FORMAT_XZ)
+            got = ora.xz_decode(blobs[c["blob"]], c["cap"])
+            assert got["res"] == 0 and got["out"][: got["dest_len"]].tobytes() == want, c["blob"]

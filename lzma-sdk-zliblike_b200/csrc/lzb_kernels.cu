@@ -97,7 +97,8 @@ template <bool kSharedModel, uint32_t G, bool kFlow>
 __global__ void __launch_bounds__(max_warps_for(G) * 32, 1)
 lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict__ out,
                         const LzbUnit *__restrict__ units, LzbResult *__restrict__ results, uint32_t n_units,
-                        uint32_t *ticket, uint32_t region_bytes, uint32_t slab_stride, uint8_t *model_slab, const LzbFlow flow)
+                        uint32_t *ticket, uint32_t region_bytes, uint32_t smem_stride, uint32_t slab_stride, uint8_t *model_slab,
+                        const LzbFlow flow)
 {
   extern __shared__ __align__(16) uint8_t lzb_smem[];
   typedef Group<G> Grp;
@@ -106,10 +107,15 @@ lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict_
   const uint32_t grp = warp * K + ((threadIdx.x & 31u) / G);               /* group index inside the CTA */
   const uint32_t groups_per_cta = (blockDim.x >> 5) * K;
   uint8_t *slab = model_slab + ((size_t)blockIdx.x * groups_per_cta + grp) * slab_stride;
-  /* shared model: region in shared memory, matched-literal trees at the start of the group's slab slice;
+  /* shared model: region in shared memory, matched-literal trees at the start of the group's slab slice --
+   * or, in a one-unit-per-warp launch whose units leave room for it (smem_stride > region_bytes), behind the
+   * region in shared memory as well: there the unit is bound by its own dependency chain, and eight dependent
+   * L2 round trips per matched literal are a large part of it;
    * global model: both in the slab slice (region first) */
-  uint8_t *region = kSharedModel ? lzb_smem + (size_t)grp * region_bytes : slab;
-  uint16_t *matched = reinterpret_cast<uint16_t *>(kSharedModel ? slab : slab + region_bytes);
+  uint8_t *region = kSharedModel ? lzb_smem + (size_t)grp * smem_stride : slab;
+  uint8_t *matched_at = kSharedModel ? slab : slab + region_bytes;
+  if (kSharedModel && G == 32 && smem_stride > region_bytes) matched_at = region + region_bytes;
+  uint16_t *matched = reinterpret_cast<uint16_t *>(matched_at);
 
   UnitDecoderT<G> d;
   LzbUnit u;
@@ -317,6 +323,7 @@ extern "C" int lzb_launch_geometry(uint32_t smem_model_bytes, uint32_t gmem_mode
   uint32_t gpart = gmem_model_bytes < lzb::kPostScratchBytes ? lzb::kPostScratchBytes : gmem_model_bytes;
   gpart = (gpart + 15u) & ~15u;
   g->region_bytes = region;
+  g->smem_stride = region;
   g->ctas = (uint32_t)g_dev_sms;
   /* lanes per unit (LZB_GROUP = 32, 16, 8 or 4) and units per SM (LZB_UNITS), both overridable for
    * measurements; defaults from profiles/r01_c_residency.md */
@@ -358,7 +365,7 @@ static cudaError_t launch_variant2(const LzbGeometry &g, uint32_t ctas, const ui
                                   const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units, uint32_t *d_ticket,
                                   uint8_t *d_slab, const LzbFlow &flow, cudaStream_t stream)
 {
-  const size_t smem = kShared ? (size_t)g.units_per_cta * g.region_bytes : 0;
+  const size_t smem = kShared ? (size_t)g.units_per_cta * g.smem_stride : 0;
   if (kShared)
   {
     cudaError_t e = cudaFuncSetAttribute(lzb::lzb_decode_units_kernel<kShared, G, kFlow>,
@@ -366,7 +373,7 @@ static cudaError_t launch_variant2(const LzbGeometry &g, uint32_t ctas, const ui
     if (e != cudaSuccess) return e;
   }
   lzb::lzb_decode_units_kernel<kShared, G, kFlow><<<ctas, g.warps_per_cta * 32, smem, stream>>>(
-      d_packed, d_out, d_units, d_results, n_units, d_ticket, g.region_bytes, g.slab_stride, d_slab, flow);
+      d_packed, d_out, d_units, d_results, n_units, d_ticket, g.region_bytes, g.smem_stride, g.slab_stride, d_slab, flow);
   return cudaGetLastError();
 }
 
@@ -414,6 +421,22 @@ extern "C" int lzb_launch_decode_flow(const uint8_t *d_packed, uint8_t *d_out, c
       g.warps_per_cta = w32;
       g.units_per_cta = w32;
     }
+  }
+  /* One unit per warp: spread the units over all SMs (a unit alone on an SM decodes 3.3 MB/s, one of sixteen
+   * 2.5 MB/s), and when the units of a CTA leave room for it in shared memory the matched-literal trees move in
+   * as well (the slab slice of the group stays unused): measured 2.62 -> 3.04 GB/s at 1,024 units of 1 MiB,
+   * 0.39 -> 0.48 GB/s at 148 (profiles/r01_j_few_units.md).  LZB_SMEM_MATCHED=0 keeps the trees in the slab and
+   * the old packing (for measurements). */
+  if (g.shared_model && g.group == 32 && !(getenv("LZB_SMEM_MATCHED") && atoi(getenv("LZB_SMEM_MATCHED")) == 0))
+  {
+    const uint32_t need = (n_units + g.ctas - 1) / g.ctas;
+    if (need < g.warps_per_cta)
+    {
+      g.warps_per_cta = need;
+      g.units_per_cta = need;
+    }
+    const uint32_t full = g.region_bytes + g.slab_stride;
+    if (g.warps_per_cta <= (uint32_t)(g_dev_smem_optin / full)) g.smem_stride = full;
   }
   uint32_t ctas = g.ctas;
   if ((uint64_t)ctas * g.units_per_cta > n_units) ctas = (n_units + g.units_per_cta - 1) / g.units_per_cta;

@@ -23,6 +23,8 @@ typedef struct LzbGeometry
   uint32_t units_per_cta;   /* resident units per SM = warps_per_cta * 32 / group        */
   uint32_t ctas;            /* one per SM                                                */
   uint32_t region_bytes;    /* shared-memory bytes per unit (model / post-pass scratch)  */
+  uint32_t smem_stride;     /* shared-memory bytes between units: region_bytes, or region_bytes + slab_stride when a
+                               one-unit-per-warp launch keeps the matched-literal trees in shared memory too */
   uint32_t slab_stride;     /* HBM slab bytes per unit (matched-literal trees, or the whole model) */
   int shared_model;
   size_t slab_bytes;        /* slab the caller must provide: ctas * units_per_cta * slab_stride */

@@ -360,6 +360,41 @@ extern "C" int lzb_launch_geometry(uint32_t smem_model_bytes, uint32_t gmem_mode
   return 0;
 }
 
+/* Launches with fewer units than warps: pure arithmetic on the default geometry (no device access, tested on the
+ * CPU in tests/test_abi_and_host.py).  regroup_allowed = LZB_GROUP not forced; dense = LZB_SMEM_MATCHED=0. */
+extern "C" void lzb_plan_few_units(LzbGeometry *gp, uint32_t n_units, size_t smem_optin, int regroup_allowed, int dense)
+{
+  LzbGeometry &g = *gp;
+  /* Few units (large LZMA2 groups, xz blocks): when every unit can have a warp of its own in one wave,
+   * sharing warps only serialises them.  The slab is sized for the default geometry, which is the larger. */
+  if (g.shared_model && g.group < 32 && regroup_allowed)
+  {
+    const uint32_t w32 = g.units_per_cta < lzb::max_warps_for(32) ? g.units_per_cta : lzb::max_warps_for(32);
+    if (n_units <= g.ctas * w32)
+    {
+      g.group = 32;
+      g.warps_per_cta = w32;
+      g.units_per_cta = w32;
+    }
+  }
+  /* One unit per warp: spread the units over all SMs (a unit alone on an SM decodes 3.3 MB/s, one of sixteen
+   * 2.5 MB/s), and when the units of a CTA leave room for it in shared memory the matched-literal trees move in
+   * as well (the slab slice of the group stays unused): measured 2.62 -> 3.04 GB/s at 1,024 units of 1 MiB,
+   * 0.39 -> 0.48 GB/s at 148 (profiles/r01_j_few_units.md).  dense keeps the trees in the slab and the old
+   * packing (for measurements). */
+  if (g.shared_model && g.group == 32 && !dense && n_units != 0)
+  {
+    const uint32_t need = (n_units + g.ctas - 1) / g.ctas;
+    if (need < g.warps_per_cta)
+    {
+      g.warps_per_cta = need;
+      g.units_per_cta = need;
+    }
+    const uint32_t full = g.region_bytes + g.slab_stride;
+    if (g.warps_per_cta <= (uint32_t)(smem_optin / full)) g.smem_stride = full;
+  }
+}
+
 template <bool kShared, uint32_t G, bool kFlow>
 static cudaError_t launch_variant2(const LzbGeometry &g, uint32_t ctas, const uint8_t *d_packed, uint8_t *d_out,
                                   const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units, uint32_t *d_ticket,
@@ -410,34 +445,8 @@ extern "C" int lzb_launch_decode_flow(const uint8_t *d_packed, uint8_t *d_out, c
   if (rc) return rc;
   if (n_units == 0) return 0;
   if (!d_model_slab) return (int)cudaErrorInvalidValue;
-  /* Few units (large LZMA2 groups, xz blocks): when every unit can have a warp of its own in one wave,
-   * sharing warps only serialises them.  The slab is sized for the default geometry, which is the larger. */
-  if (g.shared_model && g.group < 32 && !getenv("LZB_GROUP"))
-  {
-    const uint32_t w32 = g.units_per_cta < lzb::max_warps_for(32) ? g.units_per_cta : lzb::max_warps_for(32);
-    if (n_units <= g.ctas * w32)
-    {
-      g.group = 32;
-      g.warps_per_cta = w32;
-      g.units_per_cta = w32;
-    }
-  }
-  /* One unit per warp: spread the units over all SMs (a unit alone on an SM decodes 3.3 MB/s, one of sixteen
-   * 2.5 MB/s), and when the units of a CTA leave room for it in shared memory the matched-literal trees move in
-   * as well (the slab slice of the group stays unused): measured 2.62 -> 3.04 GB/s at 1,024 units of 1 MiB,
-   * 0.39 -> 0.48 GB/s at 148 (profiles/r01_j_few_units.md).  LZB_SMEM_MATCHED=0 keeps the trees in the slab and
-   * the old packing (for measurements). */
-  if (g.shared_model && g.group == 32 && !(getenv("LZB_SMEM_MATCHED") && atoi(getenv("LZB_SMEM_MATCHED")) == 0))
-  {
-    const uint32_t need = (n_units + g.ctas - 1) / g.ctas;
-    if (need < g.warps_per_cta)
-    {
-      g.warps_per_cta = need;
-      g.units_per_cta = need;
-    }
-    const uint32_t full = g.region_bytes + g.slab_stride;
-    if (g.warps_per_cta <= (uint32_t)(g_dev_smem_optin / full)) g.smem_stride = full;
-  }
+  lzb_plan_few_units(&g, n_units, g_dev_smem_optin, getenv("LZB_GROUP") == nullptr,
+                     getenv("LZB_SMEM_MATCHED") != nullptr && atoi(getenv("LZB_SMEM_MATCHED")) == 0);
   uint32_t ctas = g.ctas;
   if ((uint64_t)ctas * g.units_per_cta > n_units) ctas = (n_units + g.units_per_cta - 1) / g.units_per_cta;
   cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t), stream);

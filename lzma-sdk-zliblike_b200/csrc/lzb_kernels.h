@@ -32,6 +32,9 @@ typedef struct LzbGeometry
 
 /* Residency the decode kernel will use for a model of the given shared / HBM part sizes (bytes). */
 int lzb_launch_geometry(uint32_t smem_model_bytes, uint32_t gmem_model_bytes, LzbGeometry *g);
+/* What a launch of n_units does with that geometry when the units are fewer than the warps: one unit per warp,
+ * spread over all SMs, matched-literal trees in shared memory when they fit (pure arithmetic, no device access). */
+void lzb_plan_few_units(LzbGeometry *g, uint32_t n_units, size_t smem_optin, int regroup_allowed, int dense);
 
 /* A launch that is fed and drained while it runs (Lzb_DecodeUnitsHost): units are taken in index order, in
  * chunks of chunk_units; a unit of chunk c starts once arrived[min(c+1, n_chunks-1)] is non-zero (the packed

@@ -161,3 +161,56 @@ def test_xz_backward_index_matches_oracle(ora):
         bad[-5] ^= 1
         arr2 = (Blk * 64)()
         assert lib.Xz_ReadIndexBackward(bad.ctypes.data, len(bad), arr2, 64, C.byref(n), C.byref(ct)) == ora.xz_index(bad)["res"] != 0
+
+
+class LzbGeometry(C.Structure):       # csrc/lzb_kernels.h
+    _fields_ = [("group", C.c_uint32), ("warps_per_cta", C.c_uint32), ("units_per_cta", C.c_uint32), ("ctas", C.c_uint32),
+                ("region_bytes", C.c_uint32), ("smem_stride", C.c_uint32), ("slab_stride", C.c_uint32),
+                ("shared_model", C.c_int), ("slab_bytes", C.c_size_t)]
+
+
+def test_few_units_launch_plan():
+    """Launches with fewer units than warps (csrc/lzb_kernels.cu, profiles/r01_j_few_units.md): one unit per warp,
+    spread over all SMs, matched-literal trees in shared memory when they fit.  Pure arithmetic, no device."""
+    lib = L.load()
+    plan = lib.lzb_plan_few_units
+    plan.restype = None
+    plan.argtypes = [C.POINTER(LzbGeometry), C.c_uint32, C.c_size_t, C.c_int, C.c_int]
+    optin = 232448                                  # B200: 227 KiB per CTA
+
+    def default(region=6448, slab=8192, units=36):  # lc3/lp0/pb2: the throughput geometry of lzb_launch_geometry
+        return LzbGeometry(16, units // 2, units, 148, region, region, slab, 1, slab * units * 148)
+
+    def run(n, regroup=1, dense=0, **kw):
+        g = default(**kw)
+        plan(C.byref(g), n, optin, regroup, dense)
+        assert g.warps_per_cta * (32 // g.group) == g.units_per_cta
+        assert g.units_per_cta * g.smem_stride <= optin                   # the launch fits in shared memory
+        assert g.smem_stride in (g.region_bytes, g.region_bytes + g.slab_stride)
+        if g.group == 32:
+            assert g.ctas * g.units_per_cta >= n                          # one wave: a warp for every unit
+            assert g.units_per_cta * g.ctas * g.slab_stride <= g.slab_bytes   # inside the slab sized for the default
+        return g
+
+    g = run(65536)                                  # the bench batch: throughput mode untouched
+    assert (g.group, g.warps_per_cta, g.units_per_cta, g.smem_stride) == (16, 18, 36, 6448)
+    g = run(148 * 16 + 1)                           # one unit too many for a single wave of warps
+    assert g.group == 16
+    g = run(2220)                                   # xz4m: 15 per SM, trees fit (15 x 14,640 B)
+    assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 15, 6448 + 8192)
+    g = run(148 * 16)                               # 16 per SM: one warp each, trees stay in the slab
+    assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 16, 6448)
+    g = run(1024)                                   # spread: 7 warps on every SM instead of 16 on 64
+    assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 7, 14640)
+    for n in (1, 148):
+        g = run(n)
+        assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 1, 14640)
+    g = run(1024, dense=1)                          # LZB_SMEM_MATCHED=0: the old packing
+    assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 16, 6448)
+    g = run(1024, regroup=0)                        # LZB_GROUP forced: lanes per unit are the caller's
+    assert (g.group, g.warps_per_cta, g.smem_stride) == (16, 18, 6448)
+    # LZMA2 maxima (lc+lp = 4, pb = 4): 11,888 B region, 16 KiB of matched trees -> 8 units per SM with the trees
+    g = run(148 * 8, region=11888, slab=16384, units=18)
+    assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 8, 11888 + 16384)
+    g = run(148 * 9, region=11888, slab=16384, units=18)
+    assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 9, 11888)

@@ -109,8 +109,9 @@ lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict_
   uint8_t *slab = model_slab + ((size_t)blockIdx.x * groups_per_cta + grp) * slab_stride;
   /* shared model: region in shared memory, matched-literal trees at the start of the group's slab slice --
    * or, in a one-unit-per-warp launch whose units leave room for it (smem_stride > region_bytes), behind the
-   * region in shared memory as well: there the unit is bound by its own dependency chain, and eight dependent
-   * L2 round trips per matched literal are a large part of it;
+   * region in shared memory as well: there the unit is bound by its own dependency chain and shared memory is
+   * mostly empty, so the eight dependent L2 round trips of a matched literal are saved for free (matched
+   * literals are 2-4 % of the symbols of the bench corpora, profiles/r01_l_symbol_stats.md);
    * global model: both in the slab slice (region first) */
   uint8_t *region = kSharedModel ? lzb_smem + (size_t)grp * smem_stride : slab;
   uint8_t *matched_at = kSharedModel ? slab : slab + region_bytes;

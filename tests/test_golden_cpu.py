@@ -144,3 +144,27 @@ def test_second_opinion_liblzma_agrees_with_the_oracle(ora):
             want = lzma.decompress(blobs[c["blob"]].tobytes(), format=lzma.FORMAT_XZ)
             got = ora.xz_decode(blobs[c["blob"]], c["cap"])
             assert got["res"] == 0 and got["out"][: got["dest_len"]].tobytes() == want, c["blob"]
+
+
+def test_symbol_stats_parser_decodes_golden_streams():
+    """tools/symbol_stats.py (the analysis tool behind profiles/r01_l_symbol_stats.md) is an independent plain LZMA
+    symbol parser: its output must reproduce the golden streams' bytes (CRC recorded from the reference)."""
+    import os
+    import sys
+    import zlib
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from tools import symbol_stats
+    blobs, cs = cases.golden()
+    done = 0
+    for c in cs:
+        if not (c["kind"] == "lzma" and c["mut"] is None and c["finish"] == 0 and c["res"] == 0
+                and 0 < c["dest_len"] == c["cap"] <= 65536):
+            continue
+        props = bytes.fromhex(c["props"])
+        d = props[0]
+        lc, lp, pb = d % 9, (d // 9) % 5, d // 45
+        out, counts, _ = symbol_stats.parse(bytes(blobs[c["blob"]]), lc, lp, pb, c["cap"])
+        assert zlib.crc32(out) == c["out_crc"], c["blob"]
+        assert counts["model_bits"] > 0
+        done += 1
+    assert done >= 6

@@ -214,3 +214,35 @@ def test_few_units_launch_plan():
     assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 8, 11888 + 16384)
     g = run(148 * 9, region=11888, slab=16384, units=18)
     assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 9, 11888)
+
+
+def test_lzma2_unit_walk_fuzz_against_oracle(ora):
+    """Byte mutations of the golden LZMA2 streams (aimed at the chunk headers half of the time): the host walker
+    accepts / rejects exactly the streams the oracle's walker does and cuts the same units.  When the last chunk
+    runs past the buffer the two helpers define `end_off` differently (end of the last complete chunk here, the
+    buffer length there) -- the decode results for such streams are pinned by the golden 'cut' cases on the GPU."""
+    blobs, _ = cases.golden()
+    rng = np.random.default_rng(11)
+    rejected = 0
+    for name in ("lzma2_0", "lzma2_1", "lzma2_3", "lzma2_multi"):
+        blob = blobs[name]
+        prop = [c["prop"] for c in cases.cases_of("lzma2") if c["blob"] == name][0]
+        for _ in range(150):
+            b = blob.copy()
+            for _ in range(int(rng.integers(1, 4))):
+                pos = int(rng.integers(0, len(b))) if rng.random() < 0.4 else int(rng.integers(0, 8))
+                b[pos] = rng.integers(0, 256)
+            mine = lzb200.sdk.lzma2_index_units(b, prop)
+            want = ora.lzma2_index(b)
+            if want["n"] == -1:
+                assert mine["res"] != 0
+                rejected += 1
+                continue
+            assert mine["res"] == 0 and (mine["n"], mine["has_eos"]) == (want["n"], want["has_eos"])
+            complete = want["has_eos"] or mine["end_off"] == want["end_off"]
+            if complete:
+                assert mine["end_off"] == want["end_off"]
+                for u, w in zip(mine["units"], want["units"]):
+                    assert (u["src_off"], u["dst_cap"], u["src_len"], u["lc"]) == \
+                           (w["src_off"], w["unpack_len"], w["src_len"], w["max_lclp"])
+    assert rejected > 50

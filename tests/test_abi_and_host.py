@@ -246,3 +246,50 @@ def test_lzma2_unit_walk_fuzz_against_oracle(ora):
                     assert (u["src_off"], u["dst_cap"], u["src_len"], u["lc"]) == \
                            (w["src_off"], w["unpack_len"], w["src_len"], w["max_lclp"])
     assert rejected > 50
+
+
+def test_xz_backward_index_fuzz_against_oracle(ora):
+    """Mutations aimed at the stream footer, the index and the block headers of the golden containers: the backward
+    index reader returns the oracle's result code and, when it accepts, the same block table."""
+    lib = L.load()
+    blobs, _ = cases.golden()
+
+    class Blk(C.Structure):      # include/lzb200.h: LzbXzBlock
+        _fields_ = [("hdr_off", C.c_uint64), ("hdr_size", C.c_uint32), ("data_off", C.c_uint64),
+                    ("pack_size", C.c_uint64), ("unpack_size", C.c_uint64), ("check_off", C.c_uint64),
+                    ("expect", C.c_uint64), ("filter", C.c_int32), ("filter_param", C.c_uint32),
+                    ("lzma2_prop", C.c_uint8), ("check_type", C.c_uint8), ("complete", C.c_uint8), ("pad_", C.c_uint8),
+                    ("first_unit", C.c_uint32), ("n_units", C.c_uint32)]
+    rng = np.random.default_rng(5)
+    rejected = accepted = 0
+    for name in ("xz0", "xz1", "xz2", "xz3"):
+        xz = blobs[name]
+        hdrs = [b["hdr_off"] for b in ora.xz_index(xz)["blocks"]]
+        for _ in range(120):
+            b = xz.copy()
+            for _ in range(int(rng.integers(1, 3))):
+                r = rng.random()
+                if r < 0.5:
+                    pos = len(b) - 1 - int(rng.integers(0, 80))
+                elif r < 0.8:
+                    pos = int(hdrs[int(rng.integers(0, len(hdrs)))]) + int(rng.integers(0, 24))
+                elif r < 0.9:
+                    pos = int(rng.integers(0, 12))
+                else:
+                    pos = int(rng.integers(0, len(b)))
+                b[pos] = rng.integers(0, 256)
+            want = ora.xz_index(b)
+            arr = (Blk * 64)()
+            n, ct = C.c_size_t(0), C.c_int(0)
+            r = lib.Xz_ReadIndexBackward(b.ctypes.data, len(b), arr, 64, C.byref(n), C.byref(ct))
+            assert r == want["res"]
+            if r != 0:
+                rejected += 1
+                continue
+            accepted += 1
+            assert n.value == len(want["blocks"]) and ct.value == want["check_type"]
+            for bb, w in zip(arr[: n.value], want["blocks"]):
+                assert (bb.hdr_off, bb.hdr_size, bb.data_off, bb.pack_size, bb.unpack_size, bb.check_off) == \
+                       (w["hdr_off"], w["hdr_size"], w["data_off"], w["pack_size"], w["unpack_size"], w["check_off"])
+                assert (bb.filter, bb.filter_param, bb.lzma2_prop) == (w["filter_id"], w["filter_param"], w["lzma2_prop"])
+    assert rejected > 100 and accepted > 50

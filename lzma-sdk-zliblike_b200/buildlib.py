@@ -12,6 +12,8 @@ SO = os.path.join(LIBDIR, "liblzb200.so")
 SOURCES = ["lzb_kernels.cu", "lzb_host.cu", "lzb_containers.cu", "lzb_state.cu", "lzb_xzstream.cu", "lzb_7z.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--use_fast_math"]
+# extra nvcc flags for A/B builds of kernel experiments (forced rebuild needed); the shipped library is built without any
+NVCC_FLAGS += os.environ.get("LZB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

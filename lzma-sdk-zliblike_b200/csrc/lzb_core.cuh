@@ -142,6 +142,15 @@ template <uint32_t G> LZB_FN void group_copy_fwd(uint8_t *dic, uint32_t dst, uin
   }
 }
 
+#if defined(LZB_SMALL_LOOP) && !defined(LZB_EMU)
+template <uint32_t G> __device__ __noinline__ void group_copy_fwd_cold(uint8_t *dic, uint32_t dst, uint32_t src, uint32_t n)
+{
+  group_copy_fwd<G>(dic, dst, src, n);
+}
+#else
+#define group_copy_fwd_cold group_copy_fwd
+#endif
+
 /* plain memcpy global -> window (LZMA2 stored chunks, Lzma2Dec.c:159-162) */
 template <uint32_t G> LZB_FN void group_copy_in(uint8_t *dst, const uint8_t *src, uint32_t n)
 {
@@ -494,7 +503,20 @@ template <uint32_t G> struct UnitDecoderT
     return neg + 1u;
   }
 
+#if defined(LZB_SMALL_LOOP) && !defined(LZB_EMU)
+  /* Experiment switch, off in the shipped build (LZB_EXTRA_NVCC_FLAGS=-DLZB_SMALL_LOOP, profiles/r01_l_symbol_stats.md):
+   * length and distance-slot trees rolled and the ring-wrap copies out of line bring the symbol loop from 42.5 KB to
+   * 30.0 KB of SASS, under the 32 KB L1.5 instruction cache (same registers and spills).  Not yet timed on a GPU. */
+  template <int BITS> LZB_FN uint32_t tree_msb(uint16_t *t)
+  {
+    uint32_t sym = 1;
+#pragma unroll 1
+    for (int i = 0; i < BITS; i++) sym = (sym << 1) | rc_bit(t + sym);
+    return sym - (1u << BITS);
+  }
+#else
   template <int BITS> LZB_FN uint32_t tree_msb(uint16_t *t) { return tree_walk<BITS>(t) - (1u << BITS); }
+#endif
 
   LZB_FN uint32_t tree_lsb(uint16_t *t, uint32_t bits)
   {
@@ -578,8 +600,8 @@ template <uint32_t G> struct UnitDecoderT
     {
       /* source crosses the end of a ring dictionary (buffer interface only) */
       const uint32_t first = dic_size - src;
-      group_copy_fwd<G>(dic, dic_pos, src, first);
-      group_copy_fwd<G>(dic, dic_pos + first, 0, cur - first);
+      group_copy_fwd_cold<G>(dic, dic_pos, src, first);
+      group_copy_fwd_cold<G>(dic, dic_pos + first, 0, cur - first);
       Grp::sync();
       prev_byte = dic[dic_pos + cur - 1];
       peek_byte = dic[cur - first];

@@ -118,10 +118,16 @@ template <uint32_t G> LZB_FN void group_copy_fwd(uint8_t *dic, uint32_t dst, uin
     if (period == 1)
     {
       const uint8_t b = dic[src];
+#ifdef LZB_SMALL_LOOP
+#pragma unroll 1
+#endif
       for (uint32_t i = lane; i < n; i += G) dic[dst + i] = b;
     }
     else
     {
+#ifdef LZB_SMALL_LOOP
+#pragma unroll 1
+#endif
       for (uint32_t i = lane; i < n; i += G) dic[dst + i] = dic[src + i % period];
     }
   }
@@ -137,6 +143,9 @@ template <uint32_t G> LZB_FN void group_copy_fwd(uint8_t *dic, uint32_t dst, uin
       for (uint32_t l = 0; l < m; l++) dic[dst + base + l] = tmp[l];
     }
 #else
+#ifdef LZB_SMALL_LOOP
+#pragma unroll 1
+#endif
     for (uint32_t i = lane; i < n; i += G) dic[dst + i] = dic[src + i];
 #endif
   }
@@ -506,7 +515,8 @@ template <uint32_t G> struct UnitDecoderT
 #if defined(LZB_SMALL_LOOP) && !defined(LZB_EMU)
   /* Experiment switch, off in the shipped build (LZB_EXTRA_NVCC_FLAGS=-DLZB_SMALL_LOOP, profiles/r01_l_symbol_stats.md):
    * length and distance-slot trees rolled and the ring-wrap copies out of line bring the symbol loop from 42.5 KB to
-   * 30.0 KB of SASS, under the 32 KB L1.5 instruction cache (same registers and spills).  Not yet timed on a GPU. */
+   * 28.7 KB of SASS (with the copy loops not unrolled: 99.8 % of the matches are one trip), under the 32 KB L1.5
+   * instruction cache (same registers and spills).  Not yet timed on a GPU. */
   template <int BITS> LZB_FN uint32_t tree_msb(uint16_t *t)
   {
     uint32_t sym = 1;

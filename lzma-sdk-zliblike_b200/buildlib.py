@@ -11,7 +11,7 @@ LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "liblzb200.so")
 SOURCES = ["lzb_kernels.cu", "lzb_host.cu", "lzb_containers.cu", "lzb_state.cu", "lzb_xzstream.cu", "lzb_7z.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--use_fast_math"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 # extra nvcc flags for A/B builds of kernel experiments (forced rebuild needed); the shipped library is built without any
 NVCC_FLAGS += os.environ.get("LZB_EXTRA_NVCC_FLAGS", "").split()
 
@@ -32,25 +32,36 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile (if needed) and return the path of liblzb200.so."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, variant: str | None = None, extra_flags=()) -> str:
+    """Compile (if needed) and return the path of liblzb200.so.
+
+    variant: build an A/B copy of the library into lib/variants/<variant>/ with extra nvcc flags (kernel
+    experiments; selected at run time with LZB_LIB=<path>).  The shipped library is built without any."""
+    if variant is None and os.environ.get("LZB_LIB"):
+        return os.environ["LZB_LIB"]                    # an A/B build chosen for this process (tools/build_variant.py)
+    if variant is None and not force and not _stale():
         return SO
-    os.makedirs(LIBDIR, exist_ok=True)
+    libdir = LIBDIR if variant is None else os.path.join(LIBDIR, "variants", variant)
+    so = os.path.join(libdir, "liblzb200.so")
+    os.makedirs(libdir, exist_ok=True)
     nvcc = _nvcc()
-    objs = []
+    objs, cmds = [], []
     for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(libdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
-        subprocess.check_call(cmd)
+        cmds.append(cmd)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+    procs = [subprocess.Popen(c) for c in cmds]          # the translation units are independent: compile them side by side
+    for c, p in zip(cmds, procs):
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, c)
+    cmd = [nvcc, "-shared", "-o", so, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xlinker", "-Bsymbolic", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     subprocess.check_call(cmd)
-    return SO
+    return so
 
 
 if __name__ == "__main__":

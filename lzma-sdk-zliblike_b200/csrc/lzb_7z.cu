@@ -19,6 +19,9 @@
 
 #include <string.h>
 
+#include <memory>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -230,6 +233,7 @@ bool read_streams_info(Cursor &c, Database &db, UInt64 &data_offset, UInt32 &n_s
     {
       UInt32 n;
       if (!c.number(data_offset) || !c.number32(n) || !c.wait_for(kSize)) return false;
+      if (n > c.left) return c.fail(SZ_ERROR_ARCHIVE);          /* every size takes at least one byte */
       db.pack_sizes.resize(n);
       for (auto &s : db.pack_sizes) if (!c.number(s)) return false;
       for (;;)
@@ -245,6 +249,7 @@ bool read_streams_info(Cursor &c, Database &db, UInt64 &data_offset, UInt32 &n_s
     {
       UInt32 n;
       if (!c.wait_for(kFolder) || !c.number32(n) || !c.no_external()) return false;
+      if (n > c.left) return c.fail(SZ_ERROR_ARCHIVE);          /* every folder record takes at least one byte */
       db.folders.assign(n, Folder());
       for (auto &f : db.folders) if (!read_folder(c, f)) return false;
       if (!c.wait_for(kCodersUnpackSize)) return false;
@@ -279,7 +284,12 @@ bool read_streams_info(Cursor &c, Database &db, UInt64 &data_offset, UInt32 &n_s
         if (t == kNumUnpackStream)
         {
           n_sub = 0;
-          for (auto &f : db.folders) { if (!c.number32(f.n_streams)) return false; n_sub += f.n_streams; }
+          for (auto &f : db.folders)
+          {
+            if (!c.number32(f.n_streams)) return false;
+            if (f.n_streams > 0x7FFFFFFFu - n_sub) return c.fail(SZ_ERROR_UNSUPPORTED);
+            n_sub += f.n_streams;
+          }
           continue;
         }
         if (t == kCRC || t == kSize || t == kEnd) break;
@@ -291,10 +301,17 @@ bool read_streams_info(Cursor &c, Database &db, UInt64 &data_offset, UInt32 &n_s
         if (f.n_streams == 0) continue;
         UInt64 sum = 0;
         if (t == kSize)
-          for (UInt32 j = 1; j < f.n_streams; j++) { UInt64 s; if (!c.number(s)) return false; sub_sizes.push_back(s); sum += s; }
+          for (UInt32 j = 1; j < f.n_streams; j++)
+          {
+            UInt64 s;
+            if (!c.number(s)) return false;
+            if (s > ~sum) return c.fail(SZ_ERROR_ARCHIVE);         /* the sizes of one folder must add up without wrapping */
+            sub_sizes.push_back(s); sum += s;
+          }
         sub_sizes.push_back(f.unpack_size() - sum);      /* the last one is what is left */
       }
       if (t == kSize && !c.number(t)) return false;
+      if (t != kSize && n_sub > db.folders.size() + c.left) return c.fail(SZ_ERROR_ARCHIVE);
       sub_crc_defined.assign(n_sub, 0);
       sub_crc.assign(n_sub, 0);
       size_t listed = 0;                                  /* streams whose digest is not the folder's own */
@@ -430,6 +447,14 @@ static SRes coder_verdict(uint32_t method, UInt64 pack_size, const LzbUnit &u, c
   return used == last_end ? x.res : SZ_ERROR_DATA;
 }
 
+/* SzArEx_Extract, 7zIn.c:1390-1391: `offset + size > unpackSize` is SZ_ERROR_FAIL -- asked BEFORE anything is
+ * computed on the file's bytes, and without wrapping */
+static bool file_inside_folder(const LzbSzFile &fi, const LzbSzFolder &f)
+{
+  if (fi.out_off < f.out_off || fi.size > f.unpack_size) return false;
+  return fi.out_off - f.out_off <= f.unpack_size - fi.size;
+}
+
 static SRes decode_folders(LzbContext *ctx, const LzbSzArchive &a, const Byte *archive, size_t size, Byte *out, size_t out_bytes,
                            SRes *folder_res, SRes *file_res)
 {
@@ -465,7 +490,7 @@ static SRes decode_folders(LzbContext *ctx, const LzbSzArchive &a, const Byte *a
         if (sc.method == 0)
         {
           if (sc.pack_size != sc.unpack_size) r = SZ_ERROR_DATA;
-          else if (sc.pack_off + sc.pack_size > size) r = SZ_ERROR_INPUT_EOF;
+          else if (sc.pack_off > size || sc.pack_size > size - sc.pack_off) r = SZ_ERROR_INPUT_EOF;
           else copies.push_back({ sc.pack_off, where[ci], sc.pack_size });
         }
         else
@@ -475,7 +500,7 @@ static SRes decode_folders(LzbContext *ctx, const LzbSzArchive &a, const Byte *a
           if (r == SZ_OK) { units.push_back(u); unit_folder.push_back(i); unit_sub.push_back(ci); }
         }
       }
-      if (r == SZ_OK && (b.rc_off + b.rc_size > size)) r = SZ_ERROR_INPUT_EOF;
+      if (r == SZ_OK && (b.rc_off > size || b.rc_size > size - b.rc_off || b.rc_size > 0xFFFFFFFFull)) r = SZ_ERROR_INPUT_EOF;
       if (r == SZ_OK && f.unpack_size > 0xFFFFFFFFull) r = SZ_ERROR_UNSUPPORTED;
       if (r != SZ_OK)
       {
@@ -504,7 +529,8 @@ static SRes decode_folders(LzbContext *ctx, const LzbSzArchive &a, const Byte *a
     if (f.method == 0)
     {
       if (f.pack_size != f.unpack_size) { folder_res[i] = SZ_ERROR_DATA; continue; }
-      if (f.pack_off + f.pack_size > size) { folder_res[i] = SZ_ERROR_INPUT_EOF; continue; }
+      if (f.pack_off > size || f.pack_size > size - f.pack_off) { folder_res[i] = SZ_ERROR_INPUT_EOF; continue; }
+      if (f.unpack_size > 0xFFFFFFFFull) { lzb_set_error("7z folder larger than 4 GiB"); folder_res[i] = SZ_ERROR_UNSUPPORTED; continue; }
       copies.push_back({ f.pack_off, f.out_off, f.pack_size });
     }
     else
@@ -533,6 +559,7 @@ static SRes decode_folders(LzbContext *ctx, const LzbSzArchive &a, const Byte *a
     file_res[k] = SZ_OK;
     if (fi.folder == 0xFFFFFFFFu || !fi.has_stream || !fi.crc_defined || fi.size == 0) continue;
     if (folder_res[fi.folder] != SZ_OK) continue;
+    if (!file_inside_folder(fi, a.folders[fi.folder])) continue;          /* SZ_ERROR_FAIL below; never reaches the GPU */
     LzbUnit p;
     memset(&p, 0, sizeof p);
     p.dst_off = fi.out_off; p.dst_cap = (uint32_t)fi.size;
@@ -581,7 +608,7 @@ static SRes decode_folders(LzbContext *ctx, const LzbSzArchive &a, const Byte *a
     if (fi.folder == 0xFFFFFFFFu) { file_res[k] = SZ_OK; continue; }
     const LzbSzFolder &f = a.folders[fi.folder];
     if (folder_res[fi.folder] != SZ_OK) { file_res[k] = folder_res[fi.folder]; continue; }
-    if (fi.out_off - f.out_off + fi.size > f.unpack_size) { file_res[k] = SZ_ERROR_FAIL; continue; }
+    if (!file_inside_folder(fi, f)) { file_res[k] = SZ_ERROR_FAIL; continue; }
     if (fi.crc_defined && fi.size == 0 && fi.crc != 0) { file_res[k] = SZ_ERROR_CRC; continue; }     /* CrcCalc of nothing is 0 */
     file_res[k] = crc_bad[k] ? SZ_ERROR_CRC : SZ_OK;
   }
@@ -624,6 +651,8 @@ static SRes read_header(Cursor &c, LzbSzArchive &a, UInt64 start_after_header)
   if (type != kFilesInfo) return SZ_ERROR_ARCHIVE;
   UInt32 n_files;
   if (!c.number32(n_files)) return c.err;
+  /* a file costs the header at least one bit (its kEmptyStream flag) unless it owns one of the streams above */
+  if (n_files > 8 * (UInt64)c.left + sub_sizes.size()) return SZ_ERROR_ARCHIVE;
   a.files.assign(n_files, LzbSzFile());
   for (auto &f : a.files) { memset(&f, 0, sizeof f); f.has_stream = 1; }
   std::vector<Byte> empty_stream, empty_file, defined;
@@ -689,7 +718,7 @@ static SRes read_header(Cursor &c, LzbSzArchive &a, UInt64 start_after_header)
     }
     else
     {
-      f.is_dir = empty_file.empty() ? 1 : (empty_file[ei] ? 0 : 1);
+      f.is_dir = ei < empty_file.size() ? (empty_file[ei] ? 0 : 1) : 1;
       ei++;
     }
     if (!name_off.empty()) { f.name_off = (uint32_t)name_off[i]; f.name_len = (uint32_t)(name_off[i + 1] - name_off[i]); }
@@ -730,10 +759,16 @@ static SRes read_header(Cursor &c, LzbSzArchive &a, UInt64 start_after_header)
       a.bcj2.push_back(b);
     }
     else if (o.method == 3 && o.supported == SZ_OK) o.supported = (uint8_t)SZ_ERROR_ARCHIVE;
-    for (size_t k = 0; k < f.pack_streams.size() && pack_index + k < db.pack_sizes.size(); k++) pack_pos += db.pack_sizes[pack_index + k];
+    for (size_t k = 0; k < f.pack_streams.size() && pack_index + k < db.pack_sizes.size(); k++)
+    {
+      const UInt64 ps = db.pack_sizes[pack_index + k];
+      if (ps > ~pack_pos || o.pack_off > ~(pack_pos + ps)) return SZ_ERROR_ARCHIVE;      /* positions must not wrap */
+      pack_pos += ps;
+    }
     pack_index += f.pack_streams.size();
     o.unpack_size = f.unpack_size();
     o.out_off = out_pos;
+    if (o.unpack_size > ~out_pos) return SZ_ERROR_ARCHIVE;
     out_pos += o.unpack_size;
     o.crc = f.crc; o.crc_defined = f.crc_defined ? 1 : 0;
     o.num_streams = f.n_streams;
@@ -766,7 +801,18 @@ static SRes read_header(Cursor &c, LzbSzArchive &a, UInt64 start_after_header)
   return SZ_OK;
 }
 
+static SRes open_archive(LzbContext *ctx, const Byte *archive, size_t size, LzbSzArchive **out);
+
+/* sizes in a header are the archive's word: an allocation they make fail is SZ_ERROR_MEM (as ISzAlloc returning 0
+ * is in the reference), never an exception through the C ABI */
 extern "C" SRes SzArchive_Open(LzbContext *ctx, const Byte *archive, size_t size, LzbSzArchive **out)
+{
+  try { return open_archive(ctx, archive, size, out); }
+  catch (const std::bad_alloc &) { *out = nullptr; return SZ_ERROR_MEM; }
+  catch (const std::length_error &) { *out = nullptr; return SZ_ERROR_MEM; }
+}
+
+static SRes open_archive(LzbContext *ctx, const Byte *archive, size_t size, LzbSzArchive **out)
 {
   static const Byte k_sig[6] = { '7', 'z', 0xBC, 0xAF, 0x27, 0x1C };
   *out = nullptr;
@@ -775,8 +821,8 @@ extern "C" SRes SzArchive_Open(LzbContext *ctx, const Byte *archive, size_t size
   const UInt64 next_off = lzb_le64(archive + 12), next_size = lzb_le64(archive + 20);
   const UInt32 next_crc = lzb_le32(archive + 28);
   if (lzb_small_crc32(archive + 12, 20) != lzb_le32(archive + 8)) return SZ_ERROR_CRC;
-  LzbSzArchive *a = new LzbSzArchive();
-  if (next_size == 0) { *out = a; return SZ_OK; }
+  std::unique_ptr<LzbSzArchive> a(new LzbSzArchive());
+  if (next_size == 0) { *out = a.release(); return SZ_OK; }
   SRes res = SZ_OK;
   if (next_off > next_off + next_size || next_off > next_off + next_size + 32) res = SZ_ERROR_NO_ARCHIVE;
   else if (size < next_off || size < 32 + next_off || size < 32 + next_off + next_size) res = SZ_ERROR_INPUT_EOF;
@@ -811,6 +857,8 @@ extern "C" SRes SzArchive_Open(LzbContext *ctx, const Byte *archive, size_t size
           f.unpack_size = db.folders[0].unpack_size();
           f.crc = db.folders[0].crc; f.crc_defined = db.folders[0].crc_defined;
           tmp.folders.push_back(f);
+          if (f.unpack_size > 0xFFFFFFFFull) { res = SZ_ERROR_UNSUPPORTED; }
+          else {
           unpacked.assign((size_t)f.unpack_size + 16, 0);
           SRes fr = SZ_OK;
           res = decode_folders(ctx, tmp, archive, size, unpacked.data(), (size_t)f.unpack_size, &fr, nullptr);
@@ -820,13 +868,14 @@ extern "C" SRes SzArchive_Open(LzbContext *ctx, const Byte *archive, size_t size
             c = Cursor { unpacked.data(), (size_t)f.unpack_size };
             res = c.number(type) ? SZ_OK : c.err;
           }
+          }
         }
       }
       if (res == SZ_OK) res = type == kHeader ? read_header(c, *a, 32) : SZ_ERROR_UNSUPPORTED;
     }
   }
-  if (res != SZ_OK) { delete a; return res; }
-  *out = a;
+  if (res != SZ_OK) return res;
+  *out = a.release();
   return SZ_OK;
 }
 
@@ -842,10 +891,15 @@ extern "C" SRes SzArchive_ExtractAll(LzbContext *ctx, const LzbSzArchive *a, con
                                      SRes *folderRes, SRes *fileRes)
 {
   if (outCap < a->unpack_total) { lzb_set_error("SzArchive_ExtractAll: output smaller than SzArchive_UnpackSize"); return SZ_ERROR_PARAM; }
-  std::vector<SRes> fr(a->folders.size() + 1), fi(a->files.size() + 1);
-  const SRes r = decode_folders(ctx, *a, archive, size, out, (size_t)a->unpack_total, fr.data(), fi.data());
-  if (r != SZ_OK) return r;
-  if (folderRes) memcpy(folderRes, fr.data(), a->folders.size() * sizeof(SRes));
-  if (fileRes) memcpy(fileRes, fi.data(), a->files.size() * sizeof(SRes));
-  return SZ_OK;
+  try
+  {
+    std::vector<SRes> fr(a->folders.size() + 1), fi(a->files.size() + 1);
+    const SRes r = decode_folders(ctx, *a, archive, size, out, (size_t)a->unpack_total, fr.data(), fi.data());
+    if (r != SZ_OK) return r;
+    if (folderRes) memcpy(folderRes, fr.data(), a->folders.size() * sizeof(SRes));
+    if (fileRes) memcpy(fileRes, fi.data(), a->files.size() * sizeof(SRes));
+    return SZ_OK;
+  }
+  catch (const std::bad_alloc &) { return SZ_ERROR_MEM; }
+  catch (const std::length_error &) { return SZ_ERROR_MEM; }
 }

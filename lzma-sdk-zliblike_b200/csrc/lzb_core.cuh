@@ -601,8 +601,11 @@ template <uint32_t G> struct UnitDecoderT
       else
       {
         prev_byte = dic[src + cur - 1];
-        const uint32_t nx = src + cur;                       /* may step onto the wrap point */
-        peek_byte = (nx == dic_size) ? dic[0] : ((nx == dic_pos) ? dic[src] : dic[nx]);
+        /* dic[dicPos + cur - rep0]: wrap FIRST, then ask whether that is the first byte this copy is about to
+         * write (only when the copy starts at the wrap point, dic_pos == 0, with cur == rep0) */
+        uint32_t nx = src + cur;
+        if (nx == dic_size) nx = 0;
+        peek_byte = (nx == dic_pos) ? dic[src] : dic[nx];
       }
       group_copy_fwd<G>(dic, dic_pos, src, cur);
     }

@@ -93,10 +93,12 @@ template <uint32_t G> LZB_FN uint32_t x86_convert_group(uint8_t *data, uint32_t 
   if (lane == 0) start = 0;
   else
   {
-    /* first p >= lane*seg with no opcode candidate in [p-4, p-1] (bytes before 0 count as clean) */
+    /* first p >= lane*seg with no opcode candidate in [p-4, p-1].  Bytes before 0 count as clean only when no
+     * history is carried in: with (state & 7) != 0 the reference starts from prevPosT = -1 and the carried mask
+     * (Bra86.c:18-19), which still reaches candidates at positions 0..2 -- those belong to lane 0 alone. */
     const uint32_t nominal = lane * seg < stop ? lane * seg : stop;
     uint32_t q = nominal >= 4 ? nominal - 4 : 0;
-    uint32_t clean = 4 - (nominal - q);
+    uint32_t clean = (state & 7) != 0 ? 0u : 4 - (nominal - q);
     start = stop;
     for (; q < stop + 3; q++)
     {

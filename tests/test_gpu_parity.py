@@ -249,6 +249,24 @@ def test_filters_and_checks_large(gpu, ora):
     assert np.array_equal(np.concatenate((first, second)), one)
 
 
+def test_x86_convert_small_buffers_with_carried_state(gpu, ora):
+    """Chunked x86_Convert use: a non-zero incoming state still reaches candidates at positions 0..2 (Bra86.c:18-19),
+    which matters when the buffer is so short that the lanes' start positions fall there (5..200 bytes, all 8 states,
+    both directions)."""
+    rng = np.random.default_rng(5)
+    bad = 0
+    for n in list(range(5, 150)) + [199, 200]:
+        for rep in range(6):
+            data = rng.integers(0, 256, n, dtype=np.uint8)
+            hot = rng.random(n) < 0.35
+            data[hot] = rng.choice(np.array([0xE8, 0xE9, 0x00, 0xFF], np.uint8), int(hot.sum()))
+            st = (rep + n) & 7
+            enc = rep & 1
+            a, b = ora.x86_convert(data, 0x1000 * rep, st, enc), gpu.x86_convert(data, 0x1000 * rep, st, enc)
+            bad += not (np.array_equal(a[0], b[0]) and a[1:] == b[1:])
+    assert bad == 0
+
+
 def test_golden_lzma86_one_call(gpu):
     """Lzma86_Decode / Lzma86_GetUnpackSize (Lzma86Dec.c) vs the reference's answers: tests/golden/lzma86.json."""
     import json

@@ -132,3 +132,41 @@ def test_gpu_config1_shape_single_stream_with_ring_dictionary(ref):
         b = g.lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
         same(a, b)
         assert np.array_equal(b["out"][: len(plain)], plain)
+
+
+def ring_wrap_streams(ref, count=40):
+    """A match whose length equals its distance and that starts exactly where the ring dictionary wraps
+    (dicPos == 0, source = the last L bytes of the ring): the byte the next matched literal is compared with is the
+    FIRST byte this copy writes (LzmaDec.c:178: dic[dicPos - rep0] after the copy)."""
+    rng = np.random.default_rng(77)
+    out = []
+    for k in range(count):
+        L = int(rng.integers(2, 273))
+        head = rng.integers(0, 256, 4096, dtype=np.uint8)
+        tail = rng.integers(0, 256, int(rng.integers(8, 600)), dtype=np.uint8)
+        plain = np.concatenate((head, head[4096 - L:], tail))
+        packed, props = ref.lzma_encode(plain, level=int(rng.integers(1, 10)), dict_size=4096, end_mark=int(k & 1))
+        out.append((plain, packed, props))
+    return out
+
+
+@pytest.mark.needref
+def test_match_of_len_eq_distance_at_the_ring_wrap_under_emulation(ref):
+    for plain, packed, props in ring_wrap_streams(ref):
+        for ic, oc in ((1 << 20, 1 << 20), (4096, 4096), (997, 333)):
+            a = ref.lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
+            b = EmuStream().lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
+            same(a, b)
+            assert np.array_equal(b["out"][: len(plain)], plain)
+
+
+@pytest.mark.gpu
+@pytest.mark.needref
+def test_gpu_match_of_len_eq_distance_at_the_ring_wrap(ref):
+    g = GpuStream()
+    for plain, packed, props in ring_wrap_streams(ref, 24):
+        for ic, oc in ((1 << 20, 1 << 20), (997, 333)):
+            a = ref.lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
+            b = g.lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
+            same(a, b)
+            assert np.array_equal(b["out"][: len(plain)], plain)

@@ -1,29 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- decompressed GB/s of the B200 decode path next to the reference's CPU decode.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lzma64k|lzma2_1m|xz4m] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lzma2_8g|lzma64k|xz4m] [--extras all|none|a,b]
+                  [--impl reference]
 
-Workload (default = BASELINE.json configs[1]): a batch of 65,536 independent 64 KiB raw LZMA streams
-(LzmaUncompress contract, level 5, lc3 lp0 pb2, 64 KiB dictionary), synthetic mixed-entropy corpus
-compressed by the reference encoder.  To keep generation within seconds the batch is tiled from 2,048
-uniquely encoded streams; every tile is a physical copy (packed arena ~2.9 GB, output 4.3 GB per GPU --
-far larger than the 126 MB L2, so no step is served from cache).  A step is one pass over the batch.
+Headline workload (default) = BASELINE.json configs[2], the configuration the metric is quoted on: ONE LZMA2 stream
+of 8 GiB -- 8,192 independent 1 MiB units (dictionary reset each, Lzma2Dec.c:14-26,170-289), a single final EOS --
+strong-scaled: the host walker (Lzma2_IndexUnits) cuts the stream at the dictionary resets into ONE unit table,
+`sharding.shard_units` gives every rank a contiguous range balanced by unpacked bytes, each rank uploads only its own
+packed bytes [src_lo, src_hi) and owns the output slab [dst_lo, dst_hi).  No data-path collective.
 
-  value  : device-resident throughput -- arenas already in HBM, one fused decode launch per step
-           (Lzb_DecodeUnitsDevice), timed with CUDA events on the launching stream.
-  e2e    : the same batch through the C-ABI with HOST (pinned) arenas, H2D and D2H inside the timed
-           region (Lzb_DecodeUnitsHost).
-  N > 1  : one process per GPU (torchrun), units sharded statically, no data-path collective;
-           per-GPU work is fixed ("weak"); time = max over ranks, value = all ranks' bytes / that time.
-  --impl reference : the unmodified reference decoder (oracle/_ref/libref.so, one unit per host thread)
-           on a bounded sample of the same batch.
-Extra keys beside the contract's: `issue_roofline` (the bound that actually limits the kernel: issued warp
-instructions per SM and cycle, of 4), `e2e.per_call_ms`, and for --workload xz4m `container_e2e` (the same blocks
-as ONE .xz file through XzDecodeParallel).
+  value  : whole-job throughput, device-resident -- every rank's packed slice already in HBM, one fused decode
+           launch per rank and step (Lzb_DecodeUnitsDevice), CUDA events on the launching stream, barrier +
+           synchronize on both sides, max over ranks; 8 GiB / that time.
+  e2e    : the same job through the C-ABI with HOST (pinned) arenas, H2D and D2H inside the timed region
+           (Lzb_DecodeUnitsHost on each rank's slice); >= 1 % of the units are then CRC-checked on the host.
+  extras : one driver run also yields lines for the other BASELINE configs (key `configs`): config 2 (`weak_lzma64k`:
+           65,536 raw 64 KiB streams per GPU, replicated = weak scaling), config 4 (`xz4m`), config 5 (`7z`), config 1
+           (`lzma_stream`: one 64 MiB stream, 16 MiB ring dictionary, through LzmaDec_DecodeToBuf 64 KiB in / out).
+           Default: all of them at N = 1, `weak_lzma64k` only at N > 1.
+  --impl reference : the unmodified reference decoder (oracle/_ref/libref.so, one unit per host thread) on a
+           bounded sample of the same workload.  Rank 0 only.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -37,14 +39,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from tools.corpus import add_x86_callsites, make_corpus  # noqa: E402
+from tools.corpus import add_x86_callsites, entropy_sweep_mix, make_corpus  # noqa: E402
 
 METRIC = "decompressed GB/s"
 WORKLOADS = {
-    "lzma64k": "65,536 independent 64 KiB raw LZMA streams (LzmaUncompress), level 5, lc3 lp0 pb2, dict 64 KiB",
-    "lzma2_1m": "LZMA2 stream of independent 1 MiB units (dict reset each), level 1, dict 1 MiB, Lzma2Dec contract",
-    "xz4m": "xz container, 4 MiB blocks, x86 BCJ + LZMA2 + CRC64 per block (XzDec block path)",
+    "lzma2_8g": "ONE LZMA2 stream of 8 GiB: 8,192 independent 1 MiB units (dict reset each, 1 MiB dictionary, level 1), single "
+                "final EOS; unit table from the host walker Lzma2_IndexUnits (BASELINE configs[2])",
+    "lzma64k": "65,536 independent 64 KiB raw LZMA streams (LzmaUncompress contract), level 5, lc3 lp0 pb2, dict 64 KiB "
+               "(BASELINE configs[1])",
+    "xz4m": "xz container blocks of 4 MiB: x86 BCJ + LZMA2 (dict 4 MiB) + CRC64 per block, fused (BASELINE configs[3])",
 }
+DEFAULT_UNITS = {"lzma2_8g": 8192, "lzma64k": 65536, "xz4m": 2220}   # xz4m: 15 blocks per SM, one per warp
+UNIQUE_UNITS = {"lzma2_8g": 256, "lzma64k": 4096, "xz4m": 48}        # >= 192 MiB of uniquely encoded data each
 
 
 def env_int(name, default):
@@ -61,35 +67,42 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-# ------------------------------------------------------------------------------------ workload
-def build_workload(name: str, rank: int, cache_dir: str, small: bool):
-    """Returns dict(packed arena, unit table fields, expected per-unit CRC32, props...).  Rank 0 encodes
-    (reference encoder, all host threads) and caches under cache_dir; other ranks load the cache."""
+def log(*a):
+    if env_int("RANK", 0) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------ workloads
+def build_unique(name: str, rank: int, cache_dir: str, small: bool):
+    """The uniquely encoded units of a workload (reference encoder, all host threads).  Rank 0 encodes and caches
+    under cache_dir; other ranks load the cache."""
     from oracle import refbind
     os.makedirs(cache_dir, exist_ok=True)
-    path = os.path.join(cache_dir, f"{name}{'_small' if small else ''}.npz")
+    path = os.path.join(cache_dir, f"{name}{'_small' if small else ''}_v2.npz")
     if not os.path.exists(path):
         if rank != 0:
             raise RuntimeError("cache missing on non-zero rank")
         ref = refbind.ref()
         thr = host_threads()
+        uniq = UNIQUE_UNITS[name] // (16 if small else 1)
+        t0 = time.time()
         if name == "lzma64k":
-            uniq, unit = (256, 65536) if small else (2048, 65536)
+            unit = 65536
             corpus = make_corpus(uniq * unit, seed=1234)
             offs = np.arange(uniq, dtype=np.uint64) * unit
             lens = np.full(uniq, unit, dtype=np.uint32)
             enc = ref.encode_batch_mt(0, corpus, offs, lens, level=5, dict_size=1 << 16, lc=3, lp=0, pb=2, fb=32,
                                       end_mark=0, threads=thr)
-            kind, props = 0, enc["props"]
-        elif name == "lzma2_1m":
-            uniq, unit = (16, 1 << 20) if small else (128, 1 << 20)
+            kind = 0
+        elif name == "lzma2_8g":
+            unit = 1 << 20
             corpus = make_corpus(uniq * unit, seed=1234)
             offs = np.arange(uniq, dtype=np.uint64) * unit
             lens = np.full(uniq, unit, dtype=np.uint32)
             enc = ref.encode_batch_mt(1, corpus, offs, lens, level=1, dict_size=1 << 20, lc=3, lp=0, pb=2, threads=thr)
-            kind, props = 1, enc["props"]
+            kind = 1
         else:
-            uniq, unit = (4, 4 << 20) if small else (32, 4 << 20)
+            unit = 4 << 20
             corpus = add_x86_callsites(make_corpus(uniq * unit, seed=1234), seed=7)
             filt = np.empty_like(corpus)
             for k in range(uniq):
@@ -97,29 +110,34 @@ def build_workload(name: str, rank: int, cache_dir: str, small: bool):
             offs = np.arange(uniq, dtype=np.uint64) * unit
             lens = np.full(uniq, unit, dtype=np.uint32)
             enc = ref.encode_batch_mt(1, filt, offs, lens, level=1, dict_size=4 << 20, lc=3, lp=0, pb=2, threads=thr)
-            kind, props = 2, enc["props"]
+            kind = 2
         crcs = np.array([zlib.crc32(corpus[int(o):int(o) + int(l)].tobytes()) for o, l in zip(offs, lens)], dtype=np.uint64)
         crc64 = np.zeros(uniq, dtype=np.uint64)
         if kind == 2:
             crc64 = np.array([ref.crc64(corpus[int(o):int(o) + int(l)]) for o, l in zip(offs, lens)], dtype=np.uint64)
         blob = np.concatenate([enc["buf"][int(o):int(o) + int(l)] for o, l in zip(enc["off"], enc["len"])])
         np.savez(path + ".tmp.npz", blob=blob, plen=enc["len"], ulen=lens, crc32=crcs, crc64=crc64,
-                 props=np.asarray(props, dtype=np.uint8), kind=kind, encode_secs=enc["secs"])
+                 props=np.asarray(enc["props"], dtype=np.uint8), kind=kind, encode_secs=enc["secs"])
         os.replace(path + ".tmp.npz", path)
+        log(f"{name}: {uniq} unique units encoded in {time.time() - t0:.1f} s")
     z = np.load(path)
     return {k: z[k] for k in z.files}
 
 
-def tile_units(w, n_units: int, name: str):
-    """Physical tiling of the unique streams into the full batch: arenas + unit table (numpy)."""
+def global_layout(w, n_units: int, name: str):
+    """The whole job as ONE unit table over global arenas (numpy only; nothing is materialised here).
+    lzma2_8g: the packed arena IS the LZMA2 stream -- units back to back, one EOS byte at the end."""
     import lzb200
     R = lzb200.records
     uniq = len(w["plen"])
     idx = np.arange(n_units) % uniq
-    plen = w["plen"][idx].astype(np.uint64)
+    # lzma2_8g: every unit was encoded as a stream of its own and ends with the 0x00 end-of-stream byte; inside ONE
+    # stream only the last unit keeps it (SURVEY F2), so a unit contributes its bytes without that marker
+    trim = 1 if name == "lzma2_8g" else 0
+    plen = w["plen"][idx].astype(np.uint64) - np.uint64(trim)
     ulen = w["ulen"][idx].astype(np.uint64)
-    pad = (plen + 15) & ~np.uint64(15)
-    soff = np.concatenate(([0], np.cumsum(pad)[:-1])).astype(np.uint64)
+    step = plen if name == "lzma2_8g" else (plen + 15) & ~np.uint64(15)
+    soff = np.concatenate(([0], np.cumsum(step)[:-1])).astype(np.uint64)
     doff = np.concatenate(([0], np.cumsum(ulen)[:-1])).astype(np.uint64)
     ustart = np.concatenate(([0], np.cumsum(w["plen"].astype(np.uint64))[:-1]))
     units = R.make_units(n_units)
@@ -136,19 +154,20 @@ def tile_units(w, n_units: int, name: str):
         if kind == 2:
             units["filter"], units["check"], units["flags"] = R.FILTER_X86, R.CHECK_CRC64, R.UNIT_VERIFY
             units["expect"] = w["crc64"][idx]
-    total_p = int(soff[-1] + pad[-1]) + 64
-    total_u = int(doff[-1] + ulen[-1])
-    return dict(idx=idx, units=units, soff=soff, plen=plen, doff=doff, ulen=ulen, ustart=ustart,
-                packed_bytes=total_p, out_bytes=total_u, sum_p=int(plen.sum()), sum_u=int(ulen.sum()))
+    return dict(idx=idx, units=units, ustart=ustart, trim=trim, stream_bytes=int(soff[-1] + step[-1]) + (1 if name == "lzma2_8g" else 0),
+                sum_p=int(plen.sum()), sum_u=int(ulen.sum()))
 
 
-def fill_packed(dst: np.ndarray, w, t):
-    blob = w["blob"]
-    for i in range(len(t["idx"])):
-        k = int(t["idx"][i])
-        s, n = int(t["ustart"][k]), int(w["plen"][k])
-        o = int(t["soff"][i])
+def materialise(dst: np.ndarray, w, g, first: int, count: int, src_lo: int):
+    """Packed bytes of units [first, first + count) of the global job at their place relative to src_lo."""
+    blob, gu = w["blob"], g["units"]
+    for i in range(first, first + count):
+        k = int(g["idx"][i])
+        s, n = int(g["ustart"][k]), int(w["plen"][k]) - g["trim"]
+        o = int(gu["src_off"][i]) - src_lo
         dst[o:o + n] = blob[s:s + n]
+    if g["trim"] and first + count == len(gu):
+        dst[g["stream_bytes"] - 1 - src_lo] = 0                      # the stream's single end-of-stream byte
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -197,44 +216,355 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU legs
-def cpu_reference_run(w, t, name: str, threads: int, sample_units: int, repeat: int = 1):
+def cpu_reference_run(w, g, name: str, threads: int, sample_units: int, repeat: int = 1):
     """The unmodified reference decoder, one unit per host thread pulled from a shared counter."""
     from oracle import refbind
     ref = refbind.ref()
-    n = min(sample_units, len(t["idx"]))
+    gu = g["units"]
+    n = min(sample_units, len(gu))
     kind = int(w["kind"])
     best = None
-    packed = np.zeros(int(t["soff"][n - 1] + t["plen"][n - 1]) + 64, dtype=np.uint8)
-    sub = dict(t)
-    sub["idx"] = t["idx"][:n]
-    fill_packed(packed, w, sub)
+    soff = gu["src_off"][:n].astype(np.uint64)
+    plen = gu["src_len"][:n].astype(np.uint32)
+    doff = gu["dst_off"][:n].astype(np.uint64)
+    ulen = gu["dst_cap"][:n].astype(np.uint32)
+    packed = np.zeros(int(soff[n - 1] + plen[n - 1]) + 64, dtype=np.uint8)
+    materialise(packed, w, g, 0, n, 0)
     if kind == 2:
         # xz leg: each block wrapped as a one-block .xz member so the whole XzUnpacker path (block header,
         # LZMA2, BCJ, CRC-64, index, footer) is timed, one member per host thread
         uniq = len(w["plen"])
-        ustart = np.concatenate(([0], np.cumsum(w["plen"].astype(np.uint64))[:-1]))
+        ustart = g["ustart"]
         members = [ref.xz_assemble(w["blob"][int(ustart[k]):int(ustart[k]) + int(w["plen"][k])], [0], [int(w["plen"][k])],
-                                   [int(w["ulen"][k])], [int(w["crc64"][k])], 4, 4, 0, int(w["props"][0])) for k in range(uniq)]
-        idx = t["idx"][:n]
+                                   [int(w["ulen"][k])], [int(w["crc64"][k])], 4, 4, 0, int(w["props"][0])) for k in range(min(uniq, n))]
+        idx = g["idx"][:n]
         mlen = np.array([len(members[int(k)]) for k in idx], dtype=np.uint32)
         moff = np.concatenate(([0], np.cumsum((mlen.astype(np.uint64) + 15) & ~np.uint64(15))[:-1])).astype(np.uint64)
         arena = np.zeros(int(moff[-1]) + int(mlen[-1]) + 64, dtype=np.uint8)
         for i, k in enumerate(idx):
             arena[int(moff[i]):int(moff[i]) + int(mlen[i])] = members[int(k)]
         for _ in range(repeat):
-            r = ref.xz_decode_batch_mt(arena, moff, mlen, t["doff"][:n], t["ulen"][:n].astype(np.uint32), threads, scratch=True)
-            assert (r["res"] == 0).all() and (r["dst_done"] == t["ulen"][:n]).all(), "reference xz decode failed"
+            r = ref.xz_decode_batch_mt(arena, moff, mlen, doff, ulen, threads, scratch=True)
+            assert (r["res"] == 0).all() and (r["dst_done"] == ulen).all(), "reference xz decode failed"
             best = r["secs"] if best is None else min(best, r["secs"])
-        return dict(secs=best, out_bytes=int(t["ulen"][:n].sum()), units=n)
+        return dict(secs=best, out_bytes=int(ulen.astype(np.uint64).sum()), units=n)
     for _ in range(repeat):
-        r = ref.decode_batch_mt(0 if kind == 0 else 1, packed, t["soff"][:n], t["plen"][:n].astype(np.uint32),
-                                t["doff"][:n], t["ulen"][:n].astype(np.uint32), w["props"],
+        r = ref.decode_batch_mt(0 if kind == 0 else 1, packed, soff, plen, doff, ulen, w["props"],
                                 0 if kind == 0 else 1, threads, scratch=True)
-        assert (r["res"] == 0).all() and (r["dst_done"] == t["ulen"][:n]).all(), "reference decode failed"
-        secs = r["secs"]
-        best = secs if best is None else min(best, secs)
-    out_bytes = int(t["ulen"][:n].sum())
-    return dict(secs=best, out_bytes=out_bytes, units=n)
+        assert (r["res"] == 0).all() and (r["dst_done"] == ulen).all(), "reference decode failed"
+        best = r["secs"] if best is None else min(best, r["secs"])
+    return dict(secs=best, out_bytes=int(ulen.astype(np.uint64).sum()), units=n)
+
+
+def cpu_sample_units(name: str, threads: int, n_units: int) -> int:
+    per_thread = {"lzma64k": 512, "lzma2_8g": 16, "xz4m": 4}[name]      # ~10-20 s of CPU work on all host threads
+    return min(n_units, max(2 * threads, per_thread * threads))
+
+
+# ------------------------------------------------------------------------------------ one unit workload on the GPUs
+class Job:
+    """One unit workload, sharded (strong) or replicated (weak) over the ranks."""
+
+    def __init__(self, name, n_units, a, env, replicate=False):
+        import lzb200
+        self.name, self.a, self.env, self.replicate = name, a, env, replicate
+        rank, world, dist = env["rank"], env["world"], env["dist"]
+        if rank == 0:
+            self.w = build_unique(name, 0, env["cache"], a.small)
+        if dist:
+            dist.barrier()
+        if rank != 0:
+            self.w = build_unique(name, rank, env["cache"], a.small)
+        self.g = global_layout(self.w, n_units, name)
+        gu = self.g["units"]
+        if replicate or world == 1:
+            self.first, self.count, self.src_lo, self.dst_lo = 0, n_units, 0, 0
+            self.src_hi, self.dst_hi = self.g["stream_bytes"], self.g["sum_u"]
+            self.local = gu.copy()
+        else:
+            self.local, self.src_lo, self.src_hi, self.dst_lo, self.dst_hi, self.first = lzb200.sharding.shard_units(gu, world, rank)
+            self.count = len(self.local)
+            if name == "lzma2_8g" and rank == world - 1:
+                self.src_hi += 1                                                 # the stream's EOS byte
+        self.n_global = n_units
+
+    def stage(self):
+        """Pinned host arenas for this rank's slice; for lzma2_8g the unit table the GPU gets is the HOST WALKER's
+        (Lzma2_IndexUnits over the materialised slice of the stream), checked against the layout arithmetic."""
+        import lzb200
+        S = lzb200.sdk
+        self.h_packed = S.pinned_empty(self.src_hi - self.src_lo + 64)
+        self.h_packed[self.src_hi - self.src_lo:] = 0
+        materialise(self.h_packed, self.w, self.g, self.first, self.count, self.src_lo)
+        self.h_out = S.pinned_empty(self.dst_hi - self.dst_lo + 64)
+        self.walker = None
+        if self.name == "lzma2_8g":
+            t0 = time.perf_counter()
+            ix = S.lzma2_index_units(self.h_packed[: self.src_hi - self.src_lo], int(self.w["props"][0]), max_units=self.count + 8)
+            dt = time.perf_counter() - t0
+            wu = ix["units"]
+            same = ix["res"] == 0 and ix["n"] == self.count and all(
+                np.array_equal(wu[f], self.local[f]) for f in ("src_off", "src_len", "dst_off", "dst_cap", "dict_size", "codec"))
+            if not same:
+                raise SystemExit(f"bench.py: Lzma2_IndexUnits disagrees with the layout of the stream (res {ix['res']}, n {ix['n']} vs {self.count})")
+            self.local = wu                     # finish = the walker's "unit" mode: the last chunk's termination is validated
+            self.walker = dict(api="Lzma2_IndexUnits", units=int(ix["n"]), ms=dt * 1e3, has_eos=bool(ix["has_eos"]))
+
+    def run(self, steps, warmup, e2e=True, verify_frac=0.01):
+        import torch
+        import lzb200
+        R = lzb200.records
+        env = self.env
+        dev, ctx, dist, world = env["dev"], env["ctx"], env["dist"], env["world"]
+        units = self.local
+        n = self.count
+        max_lclp, max_pb = int((units["lc"].astype(int) + units["lp"]).max()), int(units["pb"].max())
+        pbytes = self.src_hi - self.src_lo
+        d_packed = torch.empty(pbytes + 64, dtype=torch.uint8, device=dev)
+        d_packed.copy_(torch.from_numpy(self.h_packed), non_blocking=False)
+        d_out = torch.empty(self.dst_hi - self.dst_lo + 64, dtype=torch.uint8, device=dev)
+        d_units = torch.from_numpy(units.view(np.uint8).reshape(-1)).to(dev)
+        d_results = torch.zeros(n * R.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.Stream(device=dev)      # the stream the decode kernels are launched on AND timed on
+        torch.cuda.synchronize()
+
+        def step_device(u=d_units):
+            lzb200.sdk.decode_units_device(ctx, d_packed.data_ptr(), d_out.data_ptr(), u.data_ptr(), d_results.data_ptr(), n,
+                                           max_lclp, max_pb, stream.cuda_stream)
+
+        def sync_all():
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+                torch.cuda.synchronize()
+
+        def reduce_max(x: float) -> float:
+            if not dist:
+                return x
+            tt = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        def reduce_all(flag: bool) -> bool:
+            if not dist:
+                return flag
+            tt = torch.tensor([0.0 if flag else 1.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()) == 0.0
+
+        for _ in range(warmup):
+            step_device()
+        sync_all()
+        sampler = ClockSampler(env["local"])
+        sampler.start()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record(stream)
+        for k in range(steps):
+            step_device()
+            ev[k + 1].record(stream)
+        sync_all()
+        clocks = sampler.stop()
+        my_ms = ev[0].elapsed_time(ev[-1])
+        total_ms = reduce_max(my_ms)
+        kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+        ms_per_step = total_ms / steps
+        job_bytes = self.g["sum_u"] * (world if self.replicate else 1)
+        value = job_bytes / (ms_per_step * 1e-3) / 1e9
+
+        # correctness of what was just timed (outside the timed region): statuses + every unit's CRC on the device
+        res = d_results.cpu().numpy().view(R.RESULT_DTYPE)
+        ok = bool((res["res"] == 0).all() and (res["dst_done"] == units["dst_cap"]).all())
+        vunits = units.copy()
+        lidx = self.g["idx"][self.first:self.first + n]
+        if int(self.w["kind"]) != 2:
+            vunits["check"], vunits["flags"], vunits["expect"] = R.CHECK_CRC32, R.UNIT_VERIFY, self.w["crc32"][lidx]
+        d_vunits = torch.from_numpy(vunits.view(np.uint8).reshape(-1)).to(dev)
+        step_device(d_vunits)
+        torch.cuda.synchronize()
+        vres = d_results.cpu().numpy().view(R.RESULT_DTYPE)
+        verified = reduce_all(ok and bool((vres["res"] == 0).all()))
+        del d_vunits
+
+        # e2e: host arenas through the C-ABI, copies inside the timed region
+        e2e_d = None
+        if e2e:
+            del d_out, d_packed                     # the C-ABI call owns its own device arenas
+            torch.cuda.empty_cache()
+            for _ in range(max(min(warmup, 2), 1)):
+                lzb200.sdk.decode_units_host(ctx, self.h_packed, self.h_out, units)
+            sync_all()
+            t0 = time.perf_counter()
+            per_call = []
+            for _ in range(steps):
+                tc = time.perf_counter()
+                hres = lzb200.sdk.decode_units_host(ctx, self.h_packed, self.h_out, units)
+                per_call.append((time.perf_counter() - tc) * 1e3)
+            torch.cuda.synchronize()
+            dt = reduce_max(time.perf_counter() - t0)
+            if dist:
+                dist.barrier()
+            # host-side check of the bytes the caller received: zlib.crc32 of >= 1 % of the units (evenly spread)
+            e2e_ok = bool((hres["res"] == 0).all())
+            stride = max(1, int(1.0 / max(verify_frac, 1e-6)))
+            checked = 0
+            for j in range(0, n, stride):
+                o, ln = int(units["dst_off"][j]), int(units["dst_cap"][j])
+                e2e_ok = e2e_ok and zlib.crc32(self.h_out[o:o + ln].tobytes()) == int(self.w["crc32"][lidx[j]])
+                checked += 1
+            e2e_ok = reduce_all(e2e_ok)
+            e2e_d = dict(value=job_bytes / (dt / steps) / 1e9, unit="GB/s",
+                         h2d_bytes_per_step=int(units["src_len"].astype(np.uint64).sum() + units.nbytes),
+                         d2h_bytes_per_step=int(units["dst_cap"].astype(np.uint64).sum() + res.nbytes),
+                         ms_per_step=dt / steps * 1e3, per_call_ms=[round(x, 2) for x in per_call], verified=e2e_ok,
+                         host_crc32_checked_units=checked, bytes_are="this rank's" if world > 1 else "the job's",
+                         api="Lzb_DecodeUnitsHost (pinned host arenas; one launch fed and drained while it runs)")
+        kms = float(np.mean(kernel_ms))
+        return dict(value=value, ms_per_step=ms_per_step, kernel_ms=kms, clocks=clocks, verified=verified, e2e=e2e_d,
+                    alg_bytes=int(units["src_len"].astype(np.uint64).sum() + units["dst_cap"].astype(np.uint64).sum()),
+                    units_this_rank=n, my_ms_per_step=my_ms / steps)
+
+
+def roofline_of(name: str, r: dict, geometry_note: str):
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = r["alg_bytes"] / (r["kernel_ms"] * 1e-3) / 1e9
+    traffic, tsrc = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            rec = json.load(open(tp)).get(name)
+            if rec:   # measured DRAM bytes per algorithmic byte (ncu dram__bytes_read/write.sum of this launch shape)
+                traffic = int(rec["dram_bytes_per_algorithmic_byte"] * r["alg_bytes"])
+                tsrc = rec.get("source")
+        except Exception:
+            traffic = None
+    return dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=tsrc,
+                kernel="lzb_decode_units_kernel<shared model, G lanes per unit> (rank 0's launch)", launches_per_step=1,
+                kernel_ms=r["kernel_ms"], algorithmic_bytes_per_launch=r["alg_bytes"], peak_source=peak_src,
+                note="serial range-decoder chain: bound by resident units x issue slots (and, with one unit per warp, by the "
+                     "unit's own dependency chain), far below the HBM roof. " + geometry_note)
+
+
+def geometry_note(n_units_rank: int, sms: int) -> str:
+    per_sm = n_units_rank / max(sms, 1)
+    if n_units_rank <= sms * 16:
+        return (f"{n_units_rank} units on this GPU = {per_sm:.1f} per SM: one unit per warp (lzb_decode_units_kernel<1,32,*>); the limiter is "
+                "single-unit latency, not a collective")
+    return (f"{n_units_rank} units on this GPU = {per_sm:.1f} per SM over 36 resident (two per warp, lzb_decode_units_kernel<1,16,*>): "
+            "issue-slot bound")
+
+
+# ------------------------------------------------------------------------------------ extras: configs 5 and 1
+def extra_7z(env, steps=2):
+    """BASELINE config 5 through the container API: SzArchive_Open + SzArchive_ExtractAll on a 7z archive of many
+    single-file LZMA folders (entropy sweep from byte runs to random), folder CRC-32 fused, packed header."""
+    import lzb200
+    from oracle import refbind
+    from tools import sz_writer as W
+    ref = refbind.ref()
+    thr = host_threads()
+    n_folders, file_bytes = 32768, 65536
+    parts = [make_corpus(n_folders // 16 * file_bytes, seed=500 + k, mix=entropy_sweep_mix(k / 15.0)) for k in range(16)]
+    corpus = np.concatenate(parts)
+    n = len(corpus) // file_bytes
+    offs = np.arange(n, dtype=np.uint64) * file_bytes
+    lens = np.full(n, file_bytes, dtype=np.uint32)
+    enc = ref.encode_batch_mt(0, corpus, offs, lens, level=1, dict_size=1 << 16, lc=3, lp=0, pb=2, fb=32, end_mark=0, threads=thr)
+
+    def archive_of(lo, hi):
+        folders = []
+        for i in range(lo, hi):
+            data = corpus[i * file_bytes:(i + 1) * file_bytes].tobytes()
+            f = W.Folder("lzma", [(f"d{i % 97:02d}/f{i:06d}.bin", data)])
+            f.packed = enc["buf"][int(enc["off"][i]):int(enc["off"][i]) + int(enc["len"][i])].tobytes()
+            f.props = enc["props"].tobytes()
+            f.plain = data
+            folders.append(f)
+        return W.write_archive(ref, folders, encode_header=True)
+
+    arc = np.frombuffer(archive_of(0, n), dtype=np.uint8)
+    L = lzb200.lib.load()
+    L.SzArchive_Open.restype = C.c_int
+    L.SzArchive_Open.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.SzArchive_Free.argtypes = [C.c_void_p]
+    L.SzArchive_ExtractAll.restype = C.c_int
+    L.SzArchive_ExtractAll.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    out = lzb200.sdk.pinned_empty(len(corpus) + 64)
+    harc = lzb200.sdk.pinned_empty(len(arc)); harc[:] = arc
+    fres, ires = np.zeros(n + 8, np.int32), np.zeros(n + 8, np.int32)
+    times, open_ms = [], []
+    for i in range(2 + steps):
+        t0 = time.perf_counter()
+        h = C.c_void_p(None)
+        r1 = L.SzArchive_Open(env["ctx"].h, harc.ctypes.data, len(harc), C.byref(h))
+        t1 = time.perf_counter()
+        r2 = L.SzArchive_ExtractAll(env["ctx"].h, h, harc.ctypes.data, len(harc), out.ctypes.data, len(corpus), fres.ctypes.data, ires.ctypes.data)
+        L.SzArchive_Free(h)
+        if i >= 2:
+            times.append(time.perf_counter() - t0)
+            open_ms.append((t1 - t0) * 1e3)
+        assert r1 == 0 and r2 == 0 and not fres[:n].any() and not ires[:n].any()
+    ok = zlib.crc32(out[: len(corpus)].tobytes()) == zlib.crc32(corpus.tobytes())
+    # the reference: one thread per archive (SzArEx_Extract loop), bounded sample = an archive of 512 folders spread
+    # over the entropy sweep
+    pick = np.linspace(0, n - 1, 512).astype(int)
+    folders = []
+    for i in pick:
+        data = corpus[i * file_bytes:(i + 1) * file_bytes].tobytes()
+        f = W.Folder("lzma", [(f"f{i:06d}.bin", data)])
+        f.packed = enc["buf"][int(enc["off"][i]):int(enc["off"][i]) + int(enc["len"][i])].tobytes()
+        f.props = enc["props"].tobytes()
+        f.plain = data
+        folders.append(f)
+    sub = W.write_archive(ref, folders, encode_header=True)
+    t0 = time.perf_counter()
+    r = ref.sz_extract_all(sub, out_cap=len(pick) * file_bytes + 4096, max_files=len(pick) + 8)
+    cpu = time.perf_counter() - t0
+    assert r["open_res"] == 0 and all(f["res"] == 0 for f in r["files"])
+    total = int(len(corpus))
+    lzb200.sdk.pinned_free_all()
+    return dict(workload=f"7z archive of {n} single-file LZMA folders of {file_bytes >> 10} KiB, entropy sweep byte-runs..random, packed "
+                "header, folder CRC-32 fused (BASELINE configs[4])", api="SzArchive_Open + SzArchive_ExtractAll + SzArchive_Free (pinned host buffers)",
+                value=total / float(np.mean(times)) / 1e9, unit="GB/s", e2e=True, ms_per_call=[round(x * 1e3, 1) for x in times],
+                open_ms=[round(x, 1) for x in open_ms], archive_bytes=int(len(arc)), out_bytes=total, verified=bool(ok),
+                cpu_baseline=dict(value=len(pick) * file_bytes / cpu / 1e9, unit="GB/s", cores=1, kind="reference",
+                                  sample=f"{len(pick)} folders spread over the sweep; SzArEx_Open + SzArEx_Extract per file, one thread "
+                                         "(how the reference extracts an archive)"))
+
+
+def extra_lzma_stream(env):
+    """BASELINE config 1: ONE 64 MiB raw LZMA stream, lc3 lp0 pb2, 16 MiB dictionary, decoded like LzmaUtil.c:55-106:
+    LzmaDec_Allocate + a loop over LzmaDec_DecodeToBuf with 64 KiB in / 64 KiB out.  One stream is one serial chain
+    (no parallelism to give a GPU): replicas only; the number is reported, it is not a target."""
+    import lzb200
+    from oracle import refbind
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from streamdrive import GpuStream
+    ref = refbind.ref()
+    size = (4 << 20) if env["small"] else (64 << 20)
+    plain = make_corpus(size, seed=4321)
+    level = 1                     # the match finder of level 5 needs ~40 s for 64 MiB on one thread; the decoder's work per
+    t0 = time.perf_counter()      # byte is the same order (dictionary, lc/lp/pb as LzmaUtil's defaults)
+    packed, props = ref.lzma_encode(plain, level=level, dict_size=16 << 20, end_mark=1)
+    enc_s = time.perf_counter() - t0
+    g = GpuStream()
+    t0 = time.perf_counter()
+    b = g.lzma_decode_tobuf(packed, props, len(plain), 1 << 16, 1 << 16, 0)
+    gpu_s = time.perf_counter() - t0
+    ok = b["res"] == 0 and b["dest_len"] == len(plain) and zlib.crc32(b["out"][: len(plain)].tobytes()) == zlib.crc32(plain.tobytes())
+    t0 = time.perf_counter()
+    a = ref.lzma_decode_tobuf(packed, props, len(plain), 1 << 16, 1 << 16, 0)
+    cpu_s = time.perf_counter() - t0
+    calls = (len(plain) + 65535) // 65536 + (len(packed) + 65535) // 65536
+    return dict(workload=f"one {size >> 20} MiB raw LZMA stream, lc3 lp0 pb2, 16 MiB dictionary (ring), level {level}, end mark "
+                "(BASELINE configs[0])", api="LzmaDec_Allocate + LzmaDec_DecodeToBuf loop, 64 KiB in / 64 KiB out (LzmaUtil.c:55-106)",
+                value=len(plain) / gpu_s / 1e9, unit="GB/s", e2e=True, seconds=gpu_s, calls_about=int(calls),
+                ms_per_call=gpu_s * 1e3 / max(calls, 1), verified=bool(ok and a["res"] == 0), packed_bytes=int(len(packed)), encode_seconds=enc_s,
+                cpu_baseline=dict(value=len(plain) / cpu_s / 1e9, unit="GB/s", cores=1, kind="reference", sample="the same stream, same loop"),
+                note="a single range-coded stream is one dependency chain: one warp of one SM works, replicas only")
 
 
 # ------------------------------------------------------------------------------------ main
@@ -244,41 +574,52 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="lzma64k", choices=sorted(WORKLOADS))
-    ap.add_argument("--units", type=int, default=0, help="units per GPU (default: the BASELINE size of the workload)")
+    ap.add_argument("--workload", default="lzma2_8g", choices=sorted(WORKLOADS) + ["lzma2_1m"])
+    ap.add_argument("--units", type=int, default=0, help="units of the whole job (default: the BASELINE size of the workload)")
     ap.add_argument("--small", action="store_true", help="tiny corpus, for smoke-testing the harness")
+    ap.add_argument("--weak", action="store_true", help="replicate the job on every rank instead of sharding it")
+    ap.add_argument("--extras", default="auto", help="auto | all | none | comma list of weak_lzma64k,xz4m,7z,lzma_stream")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    if a.workload == "lzma2_1m":
+        a.workload = "lzma2_8g"
 
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local = env_int("LOCAL_RANK", 0)
     cache = os.environ.get("LZB_BENCH_CACHE", "/tmp/lzb_bench_cache")
-    default_units = {"lzma64k": 65536, "lzma2_1m": 8192, "xz4m": 2220}[a.workload]   # xz4m: one 4 MiB block per resident warp
-    n_units = a.units or (default_units // 16 if a.small else default_units)
+    n_units = a.units or (DEFAULT_UNITS[a.workload] // 16 if a.small else DEFAULT_UNITS[a.workload])
     threads = host_threads()
-    cfg = dict(workload=WORKLOADS[a.workload], units_per_gpu=n_units, sharding="static, units split by rank, no collective",
-               l2="inputs >> L2 (126 MB): every tile is a physical copy", corpus="synthetic mixed-entropy, seed 1234, "
-               "reference encoder; batch tiled from uniquely encoded streams")
+    weak = a.weak
+    uniq = UNIQUE_UNITS[a.workload] // (16 if a.small else 1)
+    cfg = dict(workload=WORKLOADS[a.workload], units=n_units, unique_units=min(uniq, n_units),
+               sharding=("replicated: every rank decodes the whole table" if weak else
+                         "static: ONE unit table, contiguous ranges balanced by unpacked bytes (sharding.shard_units); each rank "
+                         "uploads only its packed slice and owns its output slab; no collective"),
+               l2="inputs >> L2 (126 MB): every tile is a physical copy",
+               corpus="synthetic mixed-entropy, seed 1234, reference encoder; the job is tiled from `unique_units` uniquely "
+                      "encoded units (copies of one unit never share a warp)")
 
     # ---------------- reference arm: CPU only, rank 0 only
     if a.impl == "reference":
         if rank != 0:
             return 0
-        w = build_workload(a.workload, 0, cache, a.small)
-        t = tile_units(w, n_units, a.workload)
-        sample = min(n_units, max(64, (512 if a.workload == "lzma64k" else 8) * threads))
-        for _ in range(max(a.warmup, 0) and 1):
-            cpu_reference_run(w, t, a.workload, threads, min(sample, 4 * threads))
-        times = [cpu_reference_run(w, t, a.workload, threads, sample) for _ in range(a.steps)]
+        w = build_unique(a.workload, 0, cache, a.small)
+        g = global_layout(w, n_units, a.workload)
+        sample = cpu_sample_units(a.workload, threads, n_units)
+        if a.warmup > 0:
+            cpu_reference_run(w, g, a.workload, threads, min(sample, 2 * threads))
+        times = [cpu_reference_run(w, g, a.workload, threads, sample) for _ in range(a.steps)]
         secs = float(np.mean([x["secs"] for x in times]))
         v = times[0]["out_bytes"] / secs / 1e9
+        cfg["sample_units"] = times[0]["units"]
         line = dict(metric=METRIC, value=v, unit="GB/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
-                    ms_per_step=secs * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8",
+                    ms_per_step=secs * 1e3, higher_is_better=True, scaling="weak" if weak else "strong", vs_baseline=None, dtype="u8",
                     data="synthetic", config=cfg, impl="reference",
                     cpu_baseline=dict(value=v, unit="GB/s", cores=threads, kind="reference",
-                                      sample=f"{times[0]['units']} units ({times[0]['out_bytes'] / 2**20:.0f} MiB out) per step, "
-                                             f"one unit per thread, unmodified LzmaDec/Lzma2Dec/XzUnpacker (oracle/_ref/libref.so)"),
+                                      sample=f"{times[0]['units']} units ({times[0]['out_bytes'] / 2**20:.0f} MiB out) per step -- a bounded "
+                                             f"sample of the job, so ms_per_step is the sample's time, not the job's -- one unit per thread, "
+                                             f"unmodified LzmaDec/Lzma2Dec/XzUnpacker (oracle/_ref/libref.so)"),
                     e2e=dict(value=v, unit="GB/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return 0
@@ -286,7 +627,6 @@ def main():
     # ---------------- B200 arm
     import torch
     import lzb200
-    from lzb200 import records as R
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
     torch.cuda.set_device(local)
@@ -295,197 +635,115 @@ def main():
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if rank == 0:
-        w = build_workload(a.workload, 0, cache, a.small)
-    if dist:
-        dist.barrier()
-    if rank != 0:
-        w = build_workload(a.workload, rank, cache, a.small)
-    t = tile_units(w, n_units, a.workload)
-    units = t["units"]
-    max_lclp, max_pb = int((units["lc"].astype(int) + units["lp"]).max()), int(units["pb"].max())
-
     ctx = lzb200.lib.Context(local)
-    h_packed = lzb200.sdk.pinned_empty(t["packed_bytes"])
-    fill_packed(h_packed, w, t)
-    h_out = lzb200.sdk.pinned_empty(t["out_bytes"] + 64)
-    dev = torch.device("cuda", local)
-    d_packed = torch.empty(t["packed_bytes"], dtype=torch.uint8, device=dev)
-    d_packed.copy_(torch.from_numpy(h_packed), non_blocking=False)
-    d_out = torch.empty(t["out_bytes"] + 64, dtype=torch.uint8, device=dev)
-    d_units = torch.from_numpy(units.view(np.uint8).reshape(-1)).to(dev)
-    d_results = torch.zeros(n_units * R.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.Stream(device=dev)      # the stream the decode kernels are launched on AND timed on
-    torch.cuda.synchronize()
+    env = dict(rank=rank, world=world, local=local, dist=dist, cache=cache, dev=torch.device("cuda", local), ctx=ctx, small=a.small)
 
-    def step_device():
-        lzb200.sdk.decode_units_device(ctx, d_packed.data_ptr(), d_out.data_ptr(), d_units.data_ptr(),
-                                       d_results.data_ptr(), n_units, max_lclp, max_pb, stream.cuda_stream)
+    t_start = time.time()
+    job = Job(a.workload, n_units, a, env, replicate=weak)
+    job.stage()
+    log(f"{a.workload}: staged {job.count} of {n_units} units on rank 0 in {time.time() - t_start:.1f} s")
+    r = job.run(a.steps, a.warmup, e2e=not a.no_e2e)
+    log(f"{a.workload}: value {r['value']:.3f} GB/s, e2e {r['e2e']['value'] if r['e2e'] else None}")
+    note = geometry_note(r["units_this_rank"], ctx.sms or 148)
+    roofline = roofline_of(a.workload, r, note)
+    cfg["units_per_gpu"] = r["units_this_rank"]
+    if job.walker:
+        cfg["unit_table"] = job.walker
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def reduce_max(x: float) -> float:
-        if not dist:
-            return x
-        tt = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
-
-    for _ in range(a.warmup):
-        step_device()
-    sync_all()
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
-    ev[0].record(stream)
-    for k in range(a.steps):
-        step_device()
-        ev[k + 1].record(stream)
-    sync_all()
-    clocks = sampler.stop()
-    total_ms = reduce_max(ev[0].elapsed_time(ev[-1]))
-    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)]
-    ms_per_step = total_ms / a.steps
-    out_bytes_all = t["sum_u"] * world
-    value = out_bytes_all / (ms_per_step * 1e-3) / 1e9
-
-    # correctness of what was just timed (outside the timed region): statuses + digest of digests
-    res = d_results.cpu().numpy().view(R.RESULT_DTYPE)
-    ok = bool((res["res"] == 0).all() and (res["dst_done"] == t["ulen"]).all())
-    vunits = units.copy()
-    if int(w["kind"]) != 2:
-        vunits["check"], vunits["flags"], vunits["expect"] = R.CHECK_CRC32, R.UNIT_VERIFY, w["crc32"][t["idx"]]
-    d_vunits = torch.from_numpy(vunits.view(np.uint8).reshape(-1)).to(dev)
-    lzb200.sdk.decode_units_device(ctx, d_packed.data_ptr(), d_out.data_ptr(), d_vunits.data_ptr(), d_results.data_ptr(),
-                                   n_units, max_lclp, max_pb, stream.cuda_stream)
-    torch.cuda.synchronize()
-    vres = d_results.cpu().numpy().view(R.RESULT_DTYPE)
-    verified = ok and bool((vres["res"] == 0).all())
-    del d_vunits
-
-    # ---------------- e2e: host arenas through the C-ABI, copies inside the timed region
-    e2e = None
-    if not a.no_e2e:
-        for _ in range(max(a.warmup, 1)):
-            lzb200.sdk.decode_units_host(ctx, h_packed, h_out, units)
-        sync_all()
-        t0 = time.perf_counter()
-        per_call = []
-        for _ in range(a.steps):
-            tc = time.perf_counter()
-            hres = lzb200.sdk.decode_units_host(ctx, h_packed, h_out, units)
-            per_call.append((time.perf_counter() - tc) * 1e3)
-        torch.cuda.synchronize()
-
-        dt = reduce_max(time.perf_counter() - t0)
-        if dist:
-            dist.barrier()
-        e2e_ok = bool((hres["res"] == 0).all())
-        k = n_units // 2
-        e2e_ok = e2e_ok and zlib.crc32(h_out[int(t["doff"][k]):int(t["doff"][k] + t["ulen"][k])].tobytes()) == int(w["crc32"][t["idx"][k]])
-        e2e = dict(value=out_bytes_all / (dt / a.steps) / 1e9, unit="GB/s",
-                   h2d_bytes_per_step=int(t["sum_p"] + units.nbytes), d2h_bytes_per_step=int(t["sum_u"] + res.nbytes),
-                   ms_per_step=dt / a.steps * 1e3, per_call_ms=[round(x, 2) for x in per_call], verified=e2e_ok,
-                   api="Lzb_DecodeUnitsHost (pinned host arenas; one launch fed and drained while it runs)")
-
-    # ---------------- xz4m only: the same blocks as ONE real .xz file through the container API (rank 0)
+    # whole-stream container call (N = 1 only): the reference-facing API on the 8 GiB stream in host memory
     container = None
-    if a.workload == "xz4m" and not a.no_e2e and rank == 0 and world == 1:
-        from oracle import refbind
-        if refbind.have_ref():
-            ref = refbind.ref()
-            nb = n_units
-            idx = t["idx"][:nb]
-            ustart = np.concatenate(([0], np.cumsum(w["plen"].astype(np.uint64))[:-1]))
-            plen = w["plen"][idx].astype(np.uint32)
-            poff = np.concatenate(([0], np.cumsum(plen.astype(np.uint64))[:-1])).astype(np.uint64)
-            blob = np.concatenate([w["blob"][int(ustart[k]):int(ustart[k]) + int(w["plen"][k])] for k in idx])
-            xz = ref.xz_assemble(blob, poff, plen, w["ulen"][idx].astype(np.uint32), w["crc64"][idx], 4, 4, 0, int(w["props"][0]))
-            total = int(w["ulen"][idx].astype(np.uint64).sum())
-            hx = lzb200.sdk.pinned_empty(len(xz)); hx[:] = xz
-            ho = lzb200.sdk.pinned_empty(total + 16)
-            times = []
-            for i in range(2 + a.steps):
-                tc = time.perf_counter()
-                d = lzb200.sdk.xz_decode(hx, total, ctx, out=ho)
-                if i >= 2:
-                    times.append(time.perf_counter() - tc)
-            okc = d["res"] == 0 and d["finished"] and d["dest_len"] == total and d["num_blocks"] == nb and \
-                zlib.crc32(d["out"][:int(w["ulen"][idx[0]])].tobytes()) == int(w["crc32"][idx[0]])
-            # the reference on one thread: timed on the first 32 blocks as a file of their own (bounded sample)
-            ns = min(nb, 32)
-            xs = ref.xz_assemble(blob[: int(poff[ns - 1]) + int(plen[ns - 1])], poff[:ns], plen[:ns], w["ulen"][idx[:ns]].astype(np.uint32),
-                                 w["crc64"][idx[:ns]], 4, 4, 0, int(w["props"][0]))
-            tot_s = int(w["ulen"][idx[:ns]].astype(np.uint64).sum())
-            t1 = time.perf_counter()
-            rr = ref.xz_decode(xs, tot_s)
-            cpu1 = time.perf_counter() - t1
-            container = dict(api="XzDecodeParallel on one .xz file (host buffers; framing on the host, all blocks in one GPU pass)",
-                             blocks=nb, file_bytes=int(len(xz)), out_bytes=total, value=total / float(np.mean(times)) / 1e9, unit="GB/s",
-                             verified=bool(okc), reference_one_thread=dict(value=tot_s / cpu1 / 1e9, unit="GB/s", res=int(rr["res"]), blocks=ns,
-                             note="the reference decodes one .xz file on one thread (XzUnpacker_Code loop)"))
-
-    # ---------------- roofline of the dominant kernel (the fused decode launch = the whole step)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    kms = float(np.mean(kernel_ms))
-    achieved = (t["sum_p"] + t["sum_u"]) / (kms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            rec = json.load(open(tp)).get(a.workload)
-            if rec:   # measured DRAM bytes per algorithmic byte (ncu --set full), scaled to this launch
-                traffic = int(rec["dram_bytes_per_algorithmic_byte"] * (t["sum_p"] + t["sum_u"]))
-        except Exception:
-            traffic = None
-    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                    kernel="lzb_decode_units_kernel<shared model, G lanes per unit>", launches_per_step=1, kernel_ms=kms,
-                    algorithmic_bytes_per_launch=int(t["sum_p"] + t["sum_u"]), peak_source=peak_src,
-                    note="serial range-decoder chain: bound by resident units x issue slots, far below the HBM roof; "
-                         "traffic above the algorithmic bytes = match sources evicted from L2 (profiles/r01_c_residency.md)")
-
-    # what actually bounds the kernel: issue slots.  Warp instructions per output byte is a
-    # property of the code + corpus measured by ncu (profiles/r01_f_final.md); the rest is measured live here.
-    issue = None
-    if a.workload == "lzma64k" and clocks.get("sm_mhz"):
-        wi_per_byte = 107.6
-        ipc = wi_per_byte * t["sum_u"] / (kms * 1e-3) / (clocks["sm_mhz"] * 1e6) / float(ctx.sms or 148)
-        issue = dict(bound="issue slots", warp_instr_per_output_byte=wi_per_byte, achieved_ipc_per_sm=ipc, peak_ipc_per_sm=4.0, frac=ipc / 4.0,
-                     source="ncu smsp__inst_executed.sum / output bytes (profiles/r01_f_final.md) x live kernel time and SM clock")
+    if a.workload == "lzma2_8g" and world == 1 and not a.no_e2e:
+        L = lzb200.lib.load()
+        total = job.g["sum_u"]
+        times = []
+        for i in range(1 + min(a.steps, 2)):
+            dl, sl, st = C.c_size_t(total), C.c_size_t(job.g["stream_bytes"]), C.c_int(0)
+            t0 = time.perf_counter()
+            rr = L.Lzma2DecodeParallel(ctx.h, job.h_out.ctypes.data, C.byref(dl), job.h_packed.ctypes.data, C.byref(sl),
+                                       int(job.w["props"][0]), 1, C.byref(st))
+            if i >= 1:
+                times.append(time.perf_counter() - t0)
+        okc = rr == 0 and st.value == 1 and dl.value == total and sl.value == job.g["stream_bytes"] and \
+            zlib.crc32(job.h_out[: 1 << 20].tobytes()) == int(job.w["crc32"][0])
+        container = dict(api="Lzma2DecodeParallel = Lzma2Dec_DecodeToDic contract on the whole stream (host buffers; chunk-header walk on "
+                             "the host, all units in one GPU pass)", value=total / float(np.mean(times)) / 1e9, unit="GB/s",
+                         res=int(rr), status=int(st.value), dest_len=int(dl.value), src_len=int(sl.value), verified=bool(okc))
 
     # ---------------- CPU baseline on this box (rank 0, N=1 only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
         from oracle import refbind
         if refbind.have_ref():
-            wc = dict(w)
-            sample = min(n_units, max(64, (512 if a.workload == "lzma64k" else 8) * threads))
-            cpu_reference_run(wc, t, a.workload, threads, min(sample, 4 * threads))
-            r = cpu_reference_run(wc, t, a.workload, threads, sample)
-            r1 = cpu_reference_run(wc, t, a.workload, 1, max(4, sample // (4 * threads)))
-            cpu = dict(value=r["out_bytes"] / r["secs"] / 1e9, unit="GB/s", cores=threads, kind="reference",
-                       one_core_value=r1["out_bytes"] / r1["secs"] / 1e9,
-                       sample=f"{r['units']} units ({r['out_bytes'] / 2**20:.0f} MiB out), one unit per thread, unmodified "
+            sample = cpu_sample_units(a.workload, threads, n_units)
+            cpu_reference_run(job.w, job.g, a.workload, threads, min(sample, 2 * threads))
+            rc = cpu_reference_run(job.w, job.g, a.workload, threads, sample)
+            r1 = cpu_reference_run(job.w, job.g, a.workload, 1, max(2, sample // (4 * threads)))
+            cpu = dict(value=rc["out_bytes"] / rc["secs"] / 1e9, unit="GB/s", cores=threads, kind="reference",
+                       one_core_value=r1["out_bytes"] / r1["secs"] / 1e9, sample_units=rc["units"],
+                       sample=f"{rc['units']} units ({rc['out_bytes'] / 2**20:.0f} MiB out), one unit per thread, unmodified "
                               f"reference decoder (oracle/_ref/libref.so), probs allocated once per thread")
+            log(f"cpu baseline {cpu['value']:.3f} GB/s on {threads} threads")
+    ratio = job.g["sum_p"] / job.g["sum_u"]
+    del job
+    lzb200.sdk.pinned_free_all()
+    torch.cuda.empty_cache()
+
+    # ---------------- the other BASELINE configs in the same run
+    if a.extras == "auto":
+        extras = ["weak_lzma64k", "xz4m", "7z", "lzma_stream"] if world == 1 else ["weak_lzma64k"]
+        if a.small or a.workload != "lzma2_8g":
+            extras = []
+    elif a.extras in ("none", ""):
+        extras = []
+    elif a.extras == "all":
+        extras = ["weak_lzma64k", "xz4m", "7z", "lzma_stream"]
+    else:
+        extras = [x for x in a.extras.split(",") if x]
+    configs = {}
+    for name in extras:
+        t0 = time.time()
+        try:
+            if name in ("weak_lzma64k", "xz4m"):
+                wl = "lzma64k" if name == "weak_lzma64k" else "xz4m"
+                j = Job(wl, DEFAULT_UNITS[wl] // (16 if a.small else 1), a, env, replicate=(name == "weak_lzma64k"))
+                j.stage()
+                rr = j.run(2, 3, e2e=not a.no_e2e)
+                d = dict(workload=WORKLOADS[wl], units_per_gpu=rr["units_this_rank"], unique_units=len(j.w["plen"]),
+                         scaling="weak (replicated per GPU)" if name == "weak_lzma64k" else "strong",
+                         value=rr["value"], unit="GB/s", ms_per_step=rr["ms_per_step"], verified=rr["verified"], e2e=rr["e2e"],
+                         roofline=roofline_of(wl, rr, geometry_note(rr["units_this_rank"], ctx.sms or 148)))
+                if rank == 0 and world == 1 and not a.no_cpu:
+                    s = cpu_sample_units(wl, threads, len(j.g["units"]))
+                    rc = cpu_reference_run(j.w, j.g, wl, threads, s)
+                    d["cpu_baseline"] = dict(value=rc["out_bytes"] / rc["secs"] / 1e9, unit="GB/s", cores=threads, kind="reference",
+                                             sample_units=rc["units"], sample=f"{rc['units']} units, one per thread")
+                del j
+                lzb200.sdk.pinned_free_all()
+                torch.cuda.empty_cache()
+            elif rank == 0:
+                d = extra_7z(env) if name == "7z" else extra_lzma_stream(env)
+            else:
+                d = None
+            if d is not None:
+                d["bench_seconds"] = round(time.time() - t0, 1)
+                configs[name] = d
+                log(f"extra {name}: {d.get('value')} GB/s in {d['bench_seconds']} s")
+        except Exception as e:                                   # an extra must never take the headline line down
+            configs[name] = dict(error=f"{type(e).__name__}: {e}")
+            log(f"extra {name} failed: {e}")
+        if dist:
+            dist.barrier()
 
     if rank == 0:
-        line = dict(metric=METRIC, value=value, unit="GB/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
-                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8",
-                    data="synthetic", config=cfg, clocks=clocks, e2e=e2e, gpu_launches=a.steps, roofline=roofline,
-                    cpu_baseline=cpu, verified=verified,
-                    ratio=dict(packed_over_unpacked=t["sum_p"] / t["sum_u"]))
+        line = dict(metric=METRIC, value=r["value"], unit="GB/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak" if weak else "strong", vs_baseline=None,
+                    dtype="u8", data="synthetic", config=cfg, clocks=r["clocks"], e2e=r["e2e"], gpu_launches=a.steps * world,
+                    roofline=roofline, cpu_baseline=cpu, verified=r["verified"],
+                    ratio=dict(packed_over_unpacked=ratio))
         if container:
             line["container_e2e"] = container
-        if issue:
-            line["issue_roofline"] = issue
+        if configs:
+            line["configs"] = configs
         print(json.dumps(line))
     if dist:
         dist.barrier()

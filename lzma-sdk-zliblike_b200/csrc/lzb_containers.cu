@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <new>
 #include <vector>
 
 enum { LZB_FINISH_UNIT = 2 };   /* internal: validate the unit's last chunk, then stop at its end */
@@ -204,26 +205,35 @@ uint32_t lzb_small_crc32_update(uint32_t reg, const Byte *p, size_t n)
 
 uint32_t lzb_small_crc32(const Byte *p, size_t n) { return ~lzb_small_crc32_update(0xFFFFFFFFu, p, n); }
 
+/* xz format 1.2, "multibyte integers": seven bits per byte, least significant group first, bit 7 set on every byte
+ * but the last, nine bytes at most; a final 0x00 that is not the only byte would be a padded (non-minimal) encoding
+ * and is refused.  Returns the encoded length, 0 when the bytes are not a valid integer (as the reference's
+ * Xz_ReadVarInt does, Xz.h:21). */
 extern "C" unsigned Xz_ReadVarInt(const Byte *p, size_t maxSize, UInt64 *value)
 {
-  /* reference XzDec.c:30-44 */
-  unsigned lim = maxSize > 9 ? 9 : (unsigned)maxSize;
-  *value = 0;
-  for (unsigned i = 0; i < lim;)
+  const size_t longest = maxSize < 9 ? maxSize : 9;
+  UInt64 v = 0;
+  unsigned len = 0;
+  bool ended = false;
+  while (len < longest && !ended)
   {
-    Byte b = p[i];
-    *value |= (UInt64)(b & 0x7F) << (7 * i++);
-    if ((b & 0x80) == 0) return (b == 0 && i != 1) ? 0 : i;
+    const Byte b = p[len];
+    v |= (UInt64)(b & 0x7Fu) << (7 * len);
+    len++;
+    ended = b < 0x80;
   }
-  return 0;
+  *value = v;
+  if (!ended) return 0;
+  if (len > 1 && p[len - 1] == 0) return 0;
+  return len;
 }
 
 extern "C" unsigned Xz_WriteVarInt(Byte *buf, UInt64 v)
 {
-  unsigned i = 0;
-  do { buf[i++] = (Byte)((v & 0x7F) | 0x80); v >>= 7; } while (v != 0);
-  buf[i - 1] &= 0x7F;
-  return i;
+  unsigned len = 0;
+  for (; v >= 0x80; v >>= 7) buf[len++] = (Byte)(v | 0x80);
+  buf[len++] = (Byte)v;
+  return len;
 }
 
 extern "C" unsigned XzFlags_GetCheckSize(CXzStreamFlags f)
@@ -240,45 +250,57 @@ extern "C" SRes Xz_ParseHeader(CXzStreamFlags *p, const Byte *buf)
   return *p <= 0xF ? SZ_OK : SZ_ERROR_UNSUPPORTED;
 }
 
-/* reference XzDec.c:505-556 */
+/* Block header, xz format 3.1:
+ *   size byte s (real size = (s + 1) * 4, the last four bytes are the CRC32 of everything before them)
+ *   block flags: bits 0-1 = number of filters - 1, bit 6 = compressed size present, bit 7 = uncompressed size present
+ *   [compressed size] [uncompressed size]           multibyte integers
+ *   per filter: id, size of properties, properties
+ *   zero padding up to the CRC32
+ * Everything wrong with a header is SZ_ERROR_ARCHIVE (what the reference's XzBlock_Parse answers, Xz.h:85). */
+namespace {
+struct HeaderFields
+{
+  const Byte *at, *end;                                   /* the bytes between the size byte and the CRC32 */
+  bool take_byte(Byte &b) { if (at == end) return false; b = *at++; return true; }
+  bool take_int(UInt64 &v)
+  {
+    const unsigned n = Xz_ReadVarInt(at, (size_t)(end - at), &v);
+    at += n;
+    return n != 0;
+  }
+  bool take_bytes(Byte *dst, UInt64 n)
+  {
+    if (n > (UInt64)(end - at)) return false;
+    memcpy(dst, at, (size_t)n);
+    at += n;
+    return true;
+  }
+  bool rest_is_zero() const { for (const Byte *q = at; q != end; q++) if (*q != 0) return false; return true; }
+};
+}  // namespace
+
 extern "C" SRes XzBlock_Parse(CXzBlock *p, const Byte *h)
 {
-  const UInt32 hs = (UInt32)h[0] << 2;
-  unsigned pos = 1;
-  if (lzb_small_crc32(h, hs) != lzb_le32(h + hs)) return SZ_ERROR_ARCHIVE;
-  if (pos == hs) return SZ_ERROR_ARCHIVE;
-  p->flags = h[pos++];
+  const UInt32 body = (UInt32)h[0] * 4;                    /* offset of the CRC32 */
+  if (lzb_le32(h + body) != lzb_small_crc32(h, body)) return SZ_ERROR_ARCHIVE;
+  HeaderFields f = { h + 1, h + body };
+  if (!f.take_byte(p->flags)) return SZ_ERROR_ARCHIVE;
   if (XzBlock_HasPackSize(p))
   {
-    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &p->packSize);
-    if (!s) return SZ_ERROR_ARCHIVE;
-    pos += s;
-    if (p->packSize == 0 || p->packSize + hs >= (UInt64)1 << 63) return SZ_ERROR_ARCHIVE;
+    /* a block holds at least one byte, and its size plus this header must stay a positive 63-bit number */
+    if (!f.take_int(p->packSize) || p->packSize == 0 || p->packSize + body >= ((UInt64)1 << 63)) return SZ_ERROR_ARCHIVE;
   }
-  if (XzBlock_HasUnpackSize(p))
+  if (XzBlock_HasUnpackSize(p) && !f.take_int(p->unpackSize)) return SZ_ERROR_ARCHIVE;
+  for (int i = 0, n = XzBlock_GetNumFilters(p); i < n; i++)
   {
-    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &p->unpackSize);
-    if (!s) return SZ_ERROR_ARCHIVE;
-    pos += s;
+    CXzFilter &flt = p->filters[i];
+    UInt64 props_bytes;
+    if (!f.take_int(flt.id) || !f.take_int(props_bytes) || props_bytes > XZ_FILTER_PROPS_SIZE_MAX ||
+        !f.take_bytes(flt.props, props_bytes))
+      return SZ_ERROR_ARCHIVE;
+    flt.propsSize = (UInt32)props_bytes;
   }
-  const int nf = XzBlock_GetNumFilters(p);
-  for (int i = 0; i < nf; i++)
-  {
-    CXzFilter &f = p->filters[i];
-    UInt64 sz;
-    unsigned s = Xz_ReadVarInt(h + pos, hs - pos, &f.id);
-    if (!s) return SZ_ERROR_ARCHIVE;
-    pos += s;
-    s = Xz_ReadVarInt(h + pos, hs - pos, &sz);
-    if (!s) return SZ_ERROR_ARCHIVE;
-    pos += s;
-    if (sz > hs - pos || sz > XZ_FILTER_PROPS_SIZE_MAX) return SZ_ERROR_ARCHIVE;
-    f.propsSize = (UInt32)sz;
-    memcpy(f.props, h + pos, (size_t)sz);
-    pos += (unsigned)sz;
-  }
-  while (pos < hs) if (h[pos++] != 0) return SZ_ERROR_ARCHIVE;
-  return SZ_OK;
+  return f.rest_is_zero() ? SZ_OK : SZ_ERROR_ARCHIVE;
 }
 
 /* Filter chains on the hot path: [x86 | delta] + LZMA2 (reference XzDec.c:63-106,356-371,558-588).
@@ -665,7 +687,8 @@ extern "C" SRes Xz_ReadIndexBackward(const Byte *src, size_t srcLen, LzbXzBlock 
   const size_t nb = (size_t)v;
   if (nb != v || nb * 2 > idx_size - 4) return SZ_ERROR_ARCHIVE;
   const unsigned csz = XzFlags_GetCheckSize((CXzStreamFlags)flags);
-  std::vector<UInt64> total(nb), unpack(nb);
+  std::vector<UInt64> total, unpack;
+  try { total.resize(nb); unpack.resize(nb); } catch (const std::bad_alloc &) { return SZ_ERROR_MEM; }
   uint64_t data_total = 0;
   for (size_t i = 0; i < nb; i++)
   {
@@ -676,6 +699,9 @@ extern "C" SRes Xz_ReadIndexBackward(const Byte *src, size_t srcLen, LzbXzBlock 
     if (!s) return SZ_ERROR_ARCHIVE;
     pos += s;
     if (total[i] == 0) return SZ_ERROR_ARCHIVE;
+    /* the blocks lie in front of the index inside this buffer: a size that does not fit there is a broken index
+     * (and must not be allowed to wrap the running sum) */
+    if (total[i] > idx_off || data_total > idx_off - total[i]) return SZ_ERROR_ARCHIVE;
     data_total += (total[i] + 3) & ~(UInt64)3;
   }
   while ((pos & 3) != 0) if (idx[pos++] != 0) return SZ_ERROR_ARCHIVE;
@@ -694,9 +720,9 @@ extern "C" SRes Xz_ReadIndexBackward(const Byte *src, size_t srcLen, LzbXzBlock 
   {
     LzbXzBlock &b = blocks[i];
     memset(&b, 0, sizeof b);
-    if (src[cur] == 0) return SZ_ERROR_ARCHIVE;
+    if (cur >= idx_off || src[cur] == 0) return SZ_ERROR_ARCHIVE;
     const UInt32 hs = ((UInt32)src[cur] << 2) + 4;
-    if (hs + csz > total[i]) return SZ_ERROR_ARCHIVE;
+    if (hs + csz > total[i] || hs > idx_off - cur) return SZ_ERROR_ARCHIVE;
     CXzBlock blk;
     memset(&blk, 0, sizeof blk);
     r = XzBlock_Parse(&blk, src + cur);

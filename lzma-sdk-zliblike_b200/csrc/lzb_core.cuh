@@ -118,16 +118,10 @@ template <uint32_t G> LZB_FN void group_copy_fwd(uint8_t *dic, uint32_t dst, uin
     if (period == 1)
     {
       const uint8_t b = dic[src];
-#ifdef LZB_SMALL_LOOP
-#pragma unroll 1
-#endif
       for (uint32_t i = lane; i < n; i += G) dic[dst + i] = b;
     }
     else
     {
-#ifdef LZB_SMALL_LOOP
-#pragma unroll 1
-#endif
       for (uint32_t i = lane; i < n; i += G) dic[dst + i] = dic[src + i % period];
     }
   }
@@ -143,22 +137,10 @@ template <uint32_t G> LZB_FN void group_copy_fwd(uint8_t *dic, uint32_t dst, uin
       for (uint32_t l = 0; l < m; l++) dic[dst + base + l] = tmp[l];
     }
 #else
-#ifdef LZB_SMALL_LOOP
-#pragma unroll 1
-#endif
     for (uint32_t i = lane; i < n; i += G) dic[dst + i] = dic[src + i];
 #endif
   }
 }
-
-#if defined(LZB_SMALL_LOOP) && !defined(LZB_EMU)
-template <uint32_t G> __device__ __noinline__ void group_copy_fwd_cold(uint8_t *dic, uint32_t dst, uint32_t src, uint32_t n)
-{
-  group_copy_fwd<G>(dic, dst, src, n);
-}
-#else
-#define group_copy_fwd_cold group_copy_fwd
-#endif
 
 /* plain memcpy global -> window (LZMA2 stored chunks, Lzma2Dec.c:159-162) */
 template <uint32_t G> LZB_FN void group_copy_in(uint8_t *dst, const uint8_t *src, uint32_t n)
@@ -296,15 +278,22 @@ static LZB_NOINLINE int peek_symbol_impl(const uint16_t *P, const uint16_t *M, c
 }
 
 /* ------------------------------------------------------------------------------------------ */
-template <uint32_t G> struct UnitDecoderT
+template <uint32_t G, bool kSmem = false, bool kAhead = false> struct UnitDecoderT
 {
   typedef Group<G> Grp;
 
   /* range coder + input window */
   uint32_t range, code;
+  /*  kAhead = false (many units per SM: issue slots are what is scarce) */
   uint32_t win;            /* upcoming input bytes, next byte in bits 31..24 */
   uint32_t win_left;       /* bytes still in `win` (1..4) */
-  uint32_t nextw;          /* raw little-endian word that follows `win` (prefetched) */
+  /*  kAhead = true (a warp per unit and SMs mostly idle: the unit's own dependency chain is what is scarce) */
+  uint32_t wlo, whi;       /* two consecutive raw (little-endian) words of the packed input               */
+  uint32_t k;              /* bytes of that pair already consumed (0..8)                                  */
+  uint32_t nb;             /* the next input byte (byte k of the pair) in bits 7..0; bits 31..8 undefined */
+  uint32_t im_pr;          /* is-match probability of the NEXT symbol, loaded while this one is still being decoded */
+  /*  both */
+  uint32_t nextw;          /* raw little-endian word that follows the window (prefetched)                 */
   const uint32_t *wbase;   /* `in` rounded down to a 4-byte boundary (pointer arithmetic keeps it a global pointer) */
   uint32_t in_skew;        /* in - wbase (0..3) */
   uint32_t widx;           /* word index `nextw` was loaded from */
@@ -312,10 +301,11 @@ template <uint32_t G> struct UnitDecoderT
   const uint8_t *in;       /* unit's packed bytes */
 
   /* model */
-  uint16_t *probs;         /* shared memory: fixed tables, pos-state tables, plain-literal trees (256/context) */
-  uint16_t *mprobs;        /* HBM (L2-resident slab): matched-literal trees (512/context), 16-byte aligned    */
+  uint16_t *probs;         /* fixed tables, pos-state tables, plain-literal trees (256/context): shared memory when kSmem */
+  uint16_t *mprobs;        /* matched-literal trees (512/context), 16-byte aligned: HBM slab (L2-resident) or shared memory */
+  uint32_t pbase;          /* model ADDRESS of probs[0]: its 32-bit shared-memory address when kSmem, else 0 (byte offset
+                            * from `probs`).  Every model access of the hot path is ld/st.shared on pbase + 2 * index. */
   uint32_t lc, lp, lp_mask, pb, pb_mask;
-  bool probs_in_smem;      /* `probs` is a shared-memory address (the usual case): enables the ld/st.shared forms */
 
   /* LZ state (CLzmaDec, LzmaDec.h:50-69) */
   uint8_t *dic;
@@ -343,28 +333,104 @@ template <uint32_t G> struct UnitDecoderT
   bool raw, want_dic, want_state, want_props;
   LzbStreamState *sst;
 
-  /* ---------------- input window ---------------- */
-  /* `win` holds the next 1..4 packed bytes (next byte on top); `nextw` is the word after it, loaded one
-   * refill ahead; `widx` is the word index nextw came from.  Consumed position = 4*widx - skew - win_left. */
-  LZB_FN uint32_t in_pos() const { return (widx << 2) - in_skew - win_left; }
+  /* ---------------- input window ----------------
+   * Two forms of the same thing (LzmaDec.c:17: "range < 2^24 => shift one input byte in"), chosen per launch:
+   *
+   * kAhead = false, launches with many units per SM.  Issued instructions are what is scarce, so the normalisation
+   *   is a compare and a branch that is taken once in eight bits (2 instructions when it is not); behind the branch a
+   *   4-byte register window (`win`, next byte on top) is shifted and, once in four bytes, refilled from `nextw`,
+   *   which is loaded one refill ahead.  Consumed position = 4 * widx - skew - win_left.
+   *
+   * kAhead = true, launches with a warp per unit and at most a few units per SM (profiles/r02_a_*: the unit's
+   *   instructions issue one every 4-5 cycles, each waiting for the one before; the branch around the normalisation
+   *   alone cost 30 cycles per bit).  Straight-line predicated code: (wlo, whi) hold eight input bytes in memory
+   *   order, `k` of them consumed, `nb` is kept ready as byte k of the pair, so a normalisation is "shift the range,
+   *   shift the byte into the code, count, pick the next byte".  top_up() -- a compare and a rarely taken branch,
+   *   placed so that at most six modelled bits (<= 5 bytes: a bit shrinks the range by less than 2^6.05) lie between
+   *   two of them -- slides the pair one word along when k >= 4.  Consumed position = 4 * (widx - 2) + k - skew. */
+  LZB_FN uint32_t in_pos() const
+  {
+    return kAhead ? ((widx - 2) << 2) + k - in_skew : (widx << 2) - in_skew - win_left;
+  }
 
   LZB_FN uint32_t load_word(uint32_t i) const { return i < wcount ? wbase[i] : 0u; }
+
+  LZB_FN uint32_t byte_at(uint32_t kk) const
+  {
+#ifdef LZB_EMU
+    return (uint32_t)(((((uint64_t)whi) << 32) | wlo) >> (8 * (kk & 7))) & 0xFFu;
+#else
+    return __byte_perm(wlo, whi, kk);                   /* selector nibble 0 = kk (0..7): byte kk of the pair */
+#endif
+  }
 
   LZB_FN void rc_seek(uint32_t pos)
   {
     const uint32_t a = in_skew + pos;
-    const uint32_t sh = a & 3;
-    widx = a >> 2;
-    win = lzb_bswap(load_word(widx)) << (8 * sh);
-    win_left = 4 - sh;
+    const uint32_t i = a >> 2;
+    if (kAhead)
+    {
+      wlo = load_word(i);
+      whi = load_word(i + 1);
+      widx = i + 2;
+      nextw = load_word(widx);
+      k = a & 3;
+      nb = byte_at(k);
+    }
+    else
+    {
+      const uint32_t sh = a & 3;
+      win = lzb_bswap(load_word(i)) << (8 * sh);
+      win_left = 4 - sh;
+      widx = i + 1;
+      nextw = load_word(widx);
+    }
+  }
+
+  LZB_FN void slide_word()
+  {
+    wlo = whi; whi = nextw; k -= 4;
     widx += 1;
     nextw = load_word(widx);
   }
 
-  /* LzmaDec.c:17.  PTX so that the common case stays at setp + bra; the groups of a warp are not in
-   * general uniform here, so these are ordinary (reconverging) branches. */
+  LZB_FN void top_up()
+  {
+    if (kAhead && k >= 4)
+    {
+      slide_word();
+      if (k >= 4) slide_word();                          /* only after five bytes in six bits */
+      nb = byte_at(k);
+    }
+  }
+
+  /* LzmaDec.c:17 */
   LZB_FN void rc_norm()
   {
+    if (kAhead)
+    {
+#ifdef LZB_EMU
+      if (range < kTop)
+      {
+        range <<= 8;
+        code = (code << 8) | (nb & 0xFFu);
+        k += 1;
+        nb = byte_at(k);
+      }
+#else
+      asm("{\n\t"
+          ".reg .pred n;\n\t"
+          "setp.lt.u32 n, %0, 0x1000000;\n\t"
+          "@n shl.b32 %0, %0, 8;\n\t"
+          "@n prmt.b32 %1, %1, %3, 0x2104;\n\t"          /* code = code << 8 | byte 0 of nb */
+          "@n add.u32 %2, %2, 1;\n\t"
+          "@n prmt.b32 %3, %4, %5, %2;\n\t"              /* nb = byte k of (wlo, whi) */
+          "}"
+          : "+r"(range), "+r"(code), "+r"(k), "+r"(nb)
+          : "r"(wlo), "r"(whi));
+#endif
+      return;
+    }
 #ifdef LZB_EMU
     if (range < kTop)
     {
@@ -380,6 +446,8 @@ template <uint32_t G> struct UnitDecoderT
       }
     }
 #else
+    /* PTX so that the common case stays at setp + bra; the groups of a warp are not in general uniform here,
+     * so these are ordinary (reconverging) branches */
     asm volatile(
         "{\n\t"
         ".reg .pred pn, pr, pe;\n\t"
@@ -408,23 +476,50 @@ template <uint32_t G> struct UnitDecoderT
 #endif
   }
 
-  /* LzmaDec.c:19-21.  Select/predicate form, no branch on the decoded bit.  Probability update with
-   * one select:  bit 0: p + ((2048 - p) >> 5) == p - ((p - 2017) >>arith 5);  bit 1: p - ((p - 0) >>arith 5). */
-  LZB_FN uint32_t rc_bit(uint16_t *p)
+  /* model access by ADDRESS (pbase + 2 * index) */
+  LZB_FN uint32_t P(uint32_t index) const { return pbase + (index << 1); }
+
+  LZB_FN uint32_t ldp(uint32_t a) const
   {
-    const uint32_t pr = *p;
-    rc_norm();
+#ifndef LZB_EMU
+    if (kSmem)
+    {
+      uint32_t v;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+      return v;
+    }
+#endif
+    return *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(probs) + a);
+  }
+
+  LZB_FN void stp(uint32_t a, uint32_t v) const
+  {
+#ifndef LZB_EMU
+    if (kSmem)
+    {
+      asm volatile("st.shared.u16 [%0], %1;" : : "r"(a), "r"(v) : "memory");
+      return;
+    }
+#endif
+    *reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(probs) + a) = (uint16_t)v;
+  }
+
+  /* LzmaDec.c:19-21 on a loaded probability: range / code step and the updated probability.  Select form, no
+   * branch on the decoded bit; returns v1 for a 1 bit, v0 for a 0 bit.  Probability update with one select:
+   * bit 0: p + ((2048 - p) >> 5) == p - ((p - 2017) >>arith 5);  bit 1: p - ((p - 0) >>arith 5). */
+  LZB_FN uint32_t bit_math(uint32_t pr, uint32_t v0, uint32_t v1, uint32_t &np)
+  {
 #ifdef LZB_EMU
     const uint32_t bound = (range >> 11) * pr;
     const bool one = code >= bound;
     const uint32_t rest = range - bound;
     range = one ? rest : bound;
     code = one ? code - bound : code;
-    const int32_t k = one ? 0 : 2017;
-    *p = (uint16_t)(pr - (uint32_t)(((int32_t)pr - k) >> 5));
-    return one ? 1u : 0u;
+    const int32_t kk = one ? 0 : 2017;
+    np = (uint16_t)(pr - (uint32_t)(((int32_t)pr - kk) >> 5));
+    return one ? v1 : v0;
 #else
-    uint32_t bit, np;
+    uint32_t c;
     asm("{\n\t"
         ".reg .pred q;\n\t"
         ".reg .u32 b, t, k;\n\t"
@@ -434,71 +529,125 @@ template <uint32_t G> struct UnitDecoderT
         "sub.u32 t, %0, b;\n\t"
         "selp.u32 %0, t, b, q;\n\t"
         "@q sub.u32 %1, %1, b;\n\t"
-        "selp.u32 %2, 1, 0, q;\n\t"
+        "selp.u32 %2, %6, %5, q;\n\t"
         "selp.u32 k, 0, 2017, q;\n\t"
         "sub.u32 k, %4, k;\n\t"
         "shr.s32 k, k, 5;\n\t"
         "sub.u32 %3, %4, k;\n\t"
         "}"
-        : "+r"(range), "+r"(code), "=r"(bit), "=r"(np)
-        : "r"(pr));
-    *p = (uint16_t)np;
-    return bit;
+        : "+r"(range), "+r"(code), "=r"(c), "=r"(np)
+        : "r"(pr), "r"(v0), "r"(v1));
+    return c;
 #endif
   }
 
-  /* Plain literal, LzmaDec.c:174: eight steps down the context's 256-entry tree.  On the GPU the walk is
-   * kept in terms of the node's 32-bit shared-memory BYTE address A (node m of a tree at L: A = L + 2m):
-   * the child address is 2A + (bit ? 2 - L : -L), one select inside the bit step + one multiply-add, where
-   * index arithmetic on m needs four instructions.  80 % of all decoded bits are of this kind (profiles/). */
-  LZB_FN uint32_t literal_plain(uint16_t *lit) { return tree_walk<8>(lit); }
+  LZB_FN uint32_t ldp32(uint32_t a) const               /* two adjacent probabilities, a 4-byte aligned */
+  {
+#ifndef LZB_EMU
+    if (kSmem)
+    {
+      uint32_t v;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+      return v;
+    }
+#endif
+    const uint16_t *q = reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(probs) + a);
+    return (uint32_t)q[0] | ((uint32_t)q[1] << 16);
+  }
 
-  /* BITS steps down a binary tree stored as t[1 .. 2^BITS): returns the node index reached (leading 1 bit kept) */
-  template <int BITS> LZB_FN uint32_t tree_walk(uint16_t *lit)
+  /* the same step with two values selected by the decoded bit */
+  LZB_FN void bit_math2(uint32_t pr, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, uint32_t &np, uint32_t &sa, uint32_t &sb)
   {
 #ifdef LZB_EMU
-    uint32_t sym = 1;
-    for (int i = 0; i < BITS; i++) sym = (sym << 1) | rc_bit(lit + sym);
-    return sym;
+    const uint32_t one = bit_math(pr, 0u, 1u, np);
+    sa = one ? a1 : a0;
+    sb = one ? b1 : b0;
 #else
-    if (!probs_in_smem)
+    asm("{\n\t"
+        ".reg .pred q;\n\t"
+        ".reg .u32 b, t, k;\n\t"
+        "shr.u32 b, %0, 11;\n\t"
+        "mul.lo.u32 b, b, %5;\n\t"
+        "setp.ge.u32 q, %1, b;\n\t"
+        "selp.u32 %2, %7, %6, q;\n\t"
+        "selp.u32 %3, %9, %8, q;\n\t"
+        "sub.u32 t, %0, b;\n\t"
+        "selp.u32 %0, t, b, q;\n\t"
+        "@q sub.u32 %1, %1, b;\n\t"
+        "selp.u32 k, 0, 2017, q;\n\t"
+        "sub.u32 k, %5, k;\n\t"
+        "shr.s32 k, k, 5;\n\t"
+        "sub.u32 %4, %5, k;\n\t"
+        "}"
+        : "+r"(range), "+r"(code), "=r"(sa), "=r"(sb), "=r"(np)
+        : "r"(pr), "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+#endif
+  }
+
+  /* one modelled bit at model address a */
+  LZB_FN uint32_t bit_sel(uint32_t a, uint32_t v0, uint32_t v1)
+  {
+    const uint32_t pr = ldp(a);
+    rc_norm();
+    uint32_t np;
+    const uint32_t c = bit_math(pr, v0, v1, np);
+    stp(a, np);
+    return c;
+  }
+  LZB_FN uint32_t rc_bit_at(uint32_t a) { return bit_sel(a, 0u, 1u); }
+
+  /* the same through a generic pointer (matched-literal trees: HBM slab or shared memory) */
+  LZB_FN uint32_t rc_bit(uint16_t *p)
+  {
+    const uint32_t pr = *p;
+    rc_norm();
+    uint32_t np;
+    const uint32_t c = bit_math(pr, 0u, 1u, np);
+    *p = (uint16_t)np;
+    return c;
+  }
+
+  /* Walks down a binary tree stored as t[1 .. 2^n), kept in terms of the node's model ADDRESS A (node m of the
+   * tree whose element 0 is at L: A = L + 2m): the child address is 2A + (bit ? 2 - L : -L) -- the bit step
+   * selects the constant, one multiply-add follows.  80 % of all decoded bits are plain-literal walks. */
+  template <int BITS> LZB_FN uint32_t tree_walk(uint32_t L)
+  {
+    if (kAhead)
     {
-      uint32_t sym = 1;
-#pragma unroll 1
-      for (int i = 0; i < BITS; i++) sym = (sym << 1) | rc_bit(lit + sym);
-      return sym;
+      /* The two children of node m sit side by side (t[2m], t[2m+1]: one aligned 32-bit word, every tree starts
+       * at an even index), so both candidates for the next step are loaded while this step's bit is still being
+       * decided: the shared-memory round trip leaves the chain, what stays is select -> multiply -> compare. */
+      uint32_t A = L + 2;
+      uint32_t pr = ldp(A);
+#pragma unroll
+      for (int i = 0; i < BITS; i++)
+      {
+        if (BITS > 6 && i == 4) top_up();
+        const uint32_t A0 = A * 2 - L;                   /* child 0; child 1 is the next entry */
+        const uint32_t pair = (i + 1 < BITS) ? ldp32(A0) : 0u;
+        rc_norm();
+        uint32_t np, nA, npr;
+        bit_math2(pr, A0, A0 + 2, pair & 0xFFFFu, pair >> 16, np, nA, npr);
+        stp(A, np);
+        A = nA;
+        pr = npr;
+      }
+      return (A - L) >> 1;
     }
-    const uint32_t L = (uint32_t)__cvta_generic_to_shared(lit);
     const uint32_t k0 = 0u - L, k1 = 2u - L;
     uint32_t A = L + 2;
 #pragma unroll
-    for (int i = 0; i < BITS; i++)
-    {
-      uint32_t pr, np, c;
-      asm volatile("ld.shared.u16 %0, [%1];" : "=r"(pr) : "r"(A) : "memory");
-      rc_norm();
-      asm("{\n\t"
-          ".reg .pred q;\n\t"
-          ".reg .u32 b, t, k;\n\t"
-          "shr.u32 b, %0, 11;\n\t"
-          "mul.lo.u32 b, b, %4;\n\t"
-          "setp.ge.u32 q, %1, b;\n\t"
-          "sub.u32 t, %0, b;\n\t"
-          "selp.u32 %0, t, b, q;\n\t"
-          "@q sub.u32 %1, %1, b;\n\t"
-          "selp.u32 %2, %6, %5, q;\n\t"
-          "selp.u32 k, 0, 2017, q;\n\t"
-          "sub.u32 k, %4, k;\n\t"
-          "shr.s32 k, k, 5;\n\t"
-          "sub.u32 %3, %4, k;\n\t"
-          "}"
-          : "+r"(range), "+r"(code), "=r"(c), "=r"(np)
-          : "r"(pr), "r"(k0), "r"(k1));
-      asm volatile("st.shared.u16 [%0], %1;" : : "r"(A), "r"(np) : "memory");
-      A = A * 2 + c;
-    }
-    return (A - L) >> 1;
-#endif
+    for (int i = 0; i < BITS; i++) A = A * 2 + bit_sel(A, k0, k1);
+    return (A - L) >> 1;                                 /* node index reached, leading 1 bit kept */
+  }
+
+  /* n more steps (n <= 6 without a top_up) from node address A; returns the node address reached */
+  LZB_FN uint32_t tree_steps(uint32_t L, uint32_t A, uint32_t n)
+  {
+    const uint32_t k0 = 0u - L, k1 = 2u - L;
+#pragma unroll 1
+    for (; n != 0; n--) A = A * 2 + bit_sel(A, k0, k1);
+    return A;
   }
 
   /* LzmaDec.c:325-334, exact wrap-around arithmetic */
@@ -512,32 +661,26 @@ template <uint32_t G> struct UnitDecoderT
     return neg + 1u;
   }
 
-#if defined(LZB_SMALL_LOOP) && !defined(LZB_EMU)
-  /* Experiment switch, off in the shipped build (LZB_EXTRA_NVCC_FLAGS=-DLZB_SMALL_LOOP, profiles/r01_l_symbol_stats.md):
-   * length and distance-slot trees rolled and the ring-wrap copies out of line bring the symbol loop from 42.5 KB to
-   * 28.7 KB of SASS (with the copy loops not unrolled: 99.8 % of the matches are one trip), under the 32 KB L1.5
-   * instruction cache (same registers and spills).  Not yet timed on a GPU. */
-  template <int BITS> LZB_FN uint32_t tree_msb(uint16_t *t)
-  {
-    uint32_t sym = 1;
-#pragma unroll 1
-    for (int i = 0; i < BITS; i++) sym = (sym << 1) | rc_bit(t + sym);
-    return sym - (1u << BITS);
-  }
-#else
-  template <int BITS> LZB_FN uint32_t tree_msb(uint16_t *t) { return tree_walk<BITS>(t) - (1u << BITS); }
-#endif
+  template <int BITS> LZB_FN uint32_t tree_msb(uint32_t index) { return tree_walk<BITS>(P(index)) - (1u << BITS); }
 
-  LZB_FN uint32_t tree_lsb(uint16_t *t, uint32_t bits)
+  /* reverse tree (LzmaDec.c:305-319,345-353): the same walk; the value is the decoded bits in reverse order */
+  static LZB_FN uint32_t reversed(uint32_t m, uint32_t bits)        /* m = 1 b0 b1 ... b(bits-1)  ->  sum of b_i << i */
   {
-    uint32_t m = 1, v = 0;
-    for (uint32_t i = 0; i < bits; i++)
-    {
-      const uint32_t b = rc_bit(t + m);
-      m = (m << 1) | b;
-      v |= b << i;
-    }
+#ifdef LZB_EMU
+    uint32_t v = 0;
+    for (uint32_t i = 0; i < bits; i++) v |= ((m >> (bits - 1 - i)) & 1u) << i;
     return v;
+#else
+    return __brev(m) >> (32 - bits);
+#endif
+  }
+  template <int BITS> LZB_FN uint32_t tree_lsb_fixed(uint32_t index) { return reversed(tree_walk<BITS>(P(index)), BITS); }
+
+  LZB_FN uint32_t tree_lsb(uint32_t index, uint32_t bits)
+  {
+    const uint32_t L = P(index);
+    const uint32_t m = (tree_steps(L, L + 2, bits) - L) >> 1;     /* 1 b0 b1 ... b(bits-1) */
+    return reversed(m, bits);
   }
 
   /* ---------------- window ---------------- */
@@ -613,8 +756,8 @@ template <uint32_t G> struct UnitDecoderT
     {
       /* source crosses the end of a ring dictionary (buffer interface only) */
       const uint32_t first = dic_size - src;
-      group_copy_fwd_cold<G>(dic, dic_pos, src, first);
-      group_copy_fwd_cold<G>(dic, dic_pos + first, 0, cur - first);
+      group_copy_fwd<G>(dic, dic_pos, src, first);
+      group_copy_fwd<G>(dic, dic_pos + first, 0, cur - first);
       Grp::sync();
       prev_byte = dic[dic_pos + cur - 1];
       peek_byte = dic[cur - first];
@@ -625,39 +768,49 @@ template <uint32_t G> struct UnitDecoderT
 
   /* One LZMA symbol: the body of LzmaDec_DecodeReal's loop, LzmaDec.c:153-410.
    * Returns 0, 1 for SZ_ERROR_DATA (nothing is committed then), 2 for the end marker.
-   * left_over receives the part of a match the output limit cut off (remainLen). */
+   * left_over receives the part of a match the output limit cut off (remainLen).
+   * top_up() calls: at most six modelled bits (or 33 direct bits) between two of them. */
   LZB_FN int decode_symbol(uint32_t limit, uint32_t &left_over)
   {
-    uint16_t *const P = probs;
     const uint32_t ps = total_pos & pb_mask;
     left_over = 0;
-    if (rc_bit(P + oVar + (state << pb) + ps) == 0)
+    top_up();
+    if (rc_bit_at(P(oVar + (state << pb) + ps)) == 0)
     {
       /* ---- literal, :161-196 ---- */
       const uint32_t ctx = ((total_pos & lp_mask) << lc) + (prev_byte >> (8 - lc));
-      uint16_t *lit = P + oVar + (56u << pb) + (ctx << 8);       /* plain tree of this context (shared) */
-      uint32_t sym = 1;
+      const uint32_t lit = P(oVar + (56u << pb) + (ctx << 8));    /* plain tree of this context */
+      uint32_t sym;
       if (state < 7)
       {
         state -= (state < 4) ? state : 3;
-        sym = literal_plain(lit);
+        sym = tree_walk<8>(lit);
       }
       else
       {
         /* matched literal (:176-192): while the decoded bits agree with the match byte the node comes
-         * from the context's matched trees (reference index 0x100 + mbit + sym -> HBM slab index
+         * from the context's matched trees (reference index 0x100 + mbit + sym -> matched-tree index
          * mbit + sym); after the first disagreement the rest of the byte uses the plain tree. */
         uint16_t *mlit = mprobs + (ctx << 9);
-        uint32_t mb = peek_byte, offs = 0x100;
+        uint32_t mb = peek_byte;
+        bool agree = true;
         state -= (state < 10) ? 3 : 6;
+        sym = 1;
 #pragma unroll 1
         for (int i = 0; i < 8; i++)
         {
-          mb <<= 1;
-          const uint32_t mbit = mb & offs;
-          const uint32_t b = rc_bit(offs ? mlit + mbit + sym : lit + sym);
+          if (i == 4) top_up();
+          uint32_t b;
+          if (agree)
+          {
+            mb <<= 1;
+            const uint32_t mbit = mb & 0x100u;
+            b = rc_bit(mlit + mbit + sym);
+            agree = (mbit >> 8) == b;
+          }
+          else
+            b = rc_bit_at(lit + (sym << 1));
           sym = (sym << 1) | b;
-          offs &= b ? mbit : ~mbit;
         }
       }
       prev_byte = sym & 0xFF;
@@ -667,7 +820,7 @@ template <uint32_t G> struct UnitDecoderT
       return 0;
     }
 
-    uint32_t is_rep = rc_bit(P + oIsRep + state);
+    uint32_t is_rep = rc_bit_at(P(oIsRep + state));
     if (is_rep == 0)
     {
       state += 12;                                   /* marker: "new distance follows", :204 */
@@ -675,9 +828,9 @@ template <uint32_t G> struct UnitDecoderT
     else
     {
       if (dict_full == 0 && total_pos == 0) return 1;                         /* :210-211 */
-      if (rc_bit(P + oRepG0 + state) == 0)
+      if (rc_bit_at(P(oRepG0 + state)) == 0)
       {
-        if (rc_bit(P + oVar + (12u << pb) + (state << pb) + ps) == 0)
+        if (rc_bit_at(P(oVar + (12u << pb) + (state << pb) + ps)) == 0)
         {
           /* ---- short rep, :219-224 ---- */
           Grp::sync();
@@ -696,10 +849,10 @@ template <uint32_t G> struct UnitDecoderT
       else
       {
         uint32_t d;
-        if (rc_bit(P + oRepG1 + state) == 0) d = rep1;
+        if (rc_bit_at(P(oRepG1 + state)) == 0) d = rep1;
         else
         {
-          if (rc_bit(P + oRepG2 + state) == 0) d = rep2;
+          if (rc_bit_at(P(oRepG2 + state)) == 0) d = rep2;
           else { d = rep3; rep3 = rep2; }
           rep2 = rep1;
         }
@@ -711,43 +864,39 @@ template <uint32_t G> struct UnitDecoderT
 
     /* ---- length, :261-292 (match and rep tables side by side) ---- */
     uint32_t len;
+    top_up();
     {
-      uint16_t *ch = P + oLenChoice + 2 * is_rep;
-      if (rc_bit(ch) == 0)
-        len = tree_msb<3>(P + oVar + (24u << pb) + ((is_rep << 3) << pb) + (ps << 3));
-      else if (rc_bit(ch + 1) == 0)
-        len = 8 + tree_msb<3>(P + oVar + (40u << pb) + ((is_rep << 3) << pb) + (ps << 3));
+      const uint32_t ch = P(oLenChoice + 2 * is_rep);
+      if (rc_bit_at(ch) == 0)
+        len = tree_msb<3>(oVar + (24u << pb) + ((is_rep << 3) << pb) + (ps << 3));
+      else if (rc_bit_at(ch + 2) == 0)
+        len = 8 + tree_msb<3>(oVar + (40u << pb) + ((is_rep << 3) << pb) + (ps << 3));
       else
-        len = 16 + tree_msb<8>(P + oLenHigh + (is_rep << 8));
+        len = 16 + tree_msb<8>(oLenHigh + (is_rep << 8));
     }
 
     if (state >= 12)
     {
       /* ---- distance, :294-374 ---- */
-      uint32_t dist = tree_msb<6>(P + oDistSlot + ((len < 4 ? len : 3u) << 6));
+      top_up();
+      uint32_t dist = tree_msb<6>(oDistSlot + ((len < 4 ? len : 3u) << 6));
       if (dist >= 4)
       {
         const uint32_t slot = dist;
         uint32_t nbits = (slot >> 1) - 1;
         dist = 2 | (slot & 1);
+        top_up();
         if (slot < 14)
         {
           dist <<= nbits;
-          dist |= tree_lsb(P + oDistSpec + dist - slot - 1, nbits);
+          dist |= tree_lsb(oDistSpec + dist - slot - 1, nbits);
         }
         else
         {
           nbits -= 4;
           do { dist = (dist << 1) + rc_direct(); } while (--nbits != 0);
-          dist <<= 4;
-          {
-            uint16_t *al = P + oDistAlign;
-            uint32_t m = 1, b;
-            b = rc_bit(al + m); m = (m << 1) | b; dist |= b;
-            b = rc_bit(al + m); m = (m << 1) | b; dist |= b << 1;
-            b = rc_bit(al + m); m = (m << 1) | b; dist |= b << 2;
-            b = rc_bit(al + m); dist |= b << 3;
-          }
+          top_up();
+          dist = (dist << 4) | tree_lsb_fixed<4>(oDistAlign);
           if (dist == 0xFFFFFFFFu)
           {
             left_over = len + kEndMarkLen;           /* end marker, :354-359 */
@@ -865,11 +1014,15 @@ template <uint32_t G> struct UnitDecoderT
 
   /* ---------------- unit set-up ---------------- */
   LZB_FN void begin(const uint8_t *packed, uint32_t packed_len, uint8_t *out, uint32_t out_cap,
-                    uint32_t dict, uint16_t *model, uint16_t *matched_model, bool model_in_smem = false)
+                    uint32_t dict, uint16_t *model, uint16_t *matched_model)
   {
     held_out = 0;
     mprobs = matched_model;
-    probs_in_smem = model_in_smem;
+#ifdef LZB_EMU
+    pbase = 0;
+#else
+    pbase = kSmem ? (uint32_t)__cvta_generic_to_shared(model) : 0u;
+#endif
     in = packed;
     in_skew = (uint32_t)((uintptr_t)packed & 3);
     wbase = reinterpret_cast<const uint32_t *>(packed - in_skew);
@@ -877,7 +1030,9 @@ template <uint32_t G> struct UnitDecoderT
     probs = model;
     dic = out; dic_size = out_cap; dic_pos = 0; dic_commit = 0;
     dict_size = dict;
-    range = code = 0; win = 0; win_left = 4; nextw = 0; widx = wcount;
+    range = code = 0; nextw = 0;
+    if (kAhead) { wlo = whi = 0; nb = 0; widx = 2; k = in_skew; im_pr = 0; }
+    else { win = 0; win_left = 4; widx = wcount; }
     state = 0; rep0 = rep1 = rep2 = rep3 = 1;
     prev_byte = peek_byte = 0;
     reset_dic_state(true, true);                                                 /* LzmaDec_Init, :701-705 */

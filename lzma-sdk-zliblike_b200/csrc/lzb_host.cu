@@ -81,6 +81,7 @@ extern "C" void Lzb_Destroy(LzbContext *c)
   if (c->h_flow) cudaFreeHost(c->h_flow);
   if (c->h_one) cudaFreeHost(c->h_one);
   if (c->flow_event) cudaEventDestroy(c->flow_event);
+  if (c->dev_event) { cudaEventSynchronize(c->dev_event); cudaEventDestroy(c->dev_event); }
   delete c;
 }
 
@@ -188,16 +189,24 @@ extern "C" SRes Lzb_DecodeUnitsDevice(LzbContext *c, const Byte *d_packed, Byte 
   if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
   const ModelBytes model = model_bytes_of(maxLcLp, maxPb);
   const size_t slab = slab_bytes_for(model);
+  if (slab > c->dev_slab_cap && c->dev_event) cudaEventSynchronize(c->dev_event);     /* never free a slab a launch still uses */
   if (slab && !grow(c->d_dev_slab, c->dev_slab_cap, slab, "cudaMalloc model slab")) return SZ_ERROR_MEM;
   cudaStream_t st = (cudaStream_t)stream;        /* NULL = the CUDA default stream, as everywhere in CUDA */
+  /* every launch of a context works in the context's ONE model slab: launches are ordered one behind the other, also
+   * across the caller's streams (an event after each launch, waited for by the next) */
+  if (!c->dev_event && !lzb_cuda_ok(cudaEventCreateWithFlags(&c->dev_event, cudaEventDisableTiming), "cudaEventCreate")) return SZ_ERROR_FAIL;
+  if (c->dev_seq != 0 && c->dev_last_stream != st && !lzb_cuda_ok(cudaStreamWaitEvent(st, c->dev_event, 0), "order launches")) return SZ_ERROR_FAIL;
   uint32_t *ticket = c->d_dev_tickets + (c->dev_seq++ % 64);
   int rc = lzb_launch_decode(d_packed, d_out, d_units, d_results, (uint32_t)n, ticket, model.smem, model.gmem, c->d_dev_slab, st);
   if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+  c->dev_last_stream = st;
+  if (!lzb_cuda_ok(cudaEventRecord(c->dev_event, st), "cudaEventRecord")) return SZ_ERROR_FAIL;
   return SZ_OK;
 }
 
 /* ------------------------------------------------------------------ host-arena batch --------- */
 struct Slice { size_t first, count; uint64_t src_lo, src_hi, dst_lo, dst_hi; };
+static const size_t kExactTailUnits = 16;
 
 /* A slice is the granule of H2D / kernel / D2H overlap.  It must still hold at least one unit per
  * resident warp (min_units), otherwise its kernel leaves the GPU partly idle. */
@@ -309,7 +318,7 @@ static SRes decode_units_flow(LzbContext *c, const Byte *packed, size_t packedBy
   if (!ok) { *h_abort = 1; }
   if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
   /* drain: as chunks complete */
-  const bool trace = getenv("LZB_FLOW_TRACE") != nullptr;
+  static const bool trace = getenv("LZB_FLOW_TRACE") != nullptr;
   const auto t_start = std::chrono::steady_clock::now();
   auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
   if (trace) fprintf(stderr, "[flow] %zu units, %zu chunks of %zu units; fed at %.2f ms\n", n, n_chunks, chunk_units, ms_since());
@@ -380,7 +389,7 @@ static bool flow_eligible(LzbContext *c, const Byte *packed, size_t packedBytes,
                           const LzbUnit *units, size_t n, uint64_t total_out)
 {
   size_t free_b = 0, total_b = 0;
-  const char *mode = getenv("LZB_FLOW");
+  static const char *const mode = getenv("LZB_FLOW");
   const bool want = !c->flow_off && (mode ? atoi(mode) != 0 : total_out >= (256ull << 20));
   /* page-locked arenas only: copies from pageable memory block the calling thread, which must stay free to
    * feed and drain the launch */
@@ -432,7 +441,8 @@ extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t pa
   uint64_t total_out = 0;
   for (size_t i = 0; i < n; i++)
   {
-    if (units[i].src_off + units[i].src_len > packedBytes || units[i].dst_off + units[i].dst_cap > outBytes)
+    if (units[i].src_len > packedBytes || units[i].src_off > packedBytes - units[i].src_len ||
+        units[i].dst_cap > outBytes || units[i].dst_off > outBytes - units[i].dst_cap)
     { lzb_set_error("unit %zu exceeds its arena", i); return SZ_ERROR_PARAM; }
     total_out += units[i].dst_cap;
   }
@@ -502,7 +512,25 @@ extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t pa
     if (!ok) { ret = SZ_ERROR_FAIL; break; }
     int rc = lzb_launch_decode(s.d_packed, s.d_out, s.d_units, s.d_results, (uint32_t)sl.count, s.d_ticket, model.smem, model.gmem, s.d_slab, s.stream);
     if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); ret = SZ_ERROR_FAIL; break; }
-    /* D2H: one copy per maximal run of units whose outputs tile the arena (never touch the gaps) */
+    if (sl.count <= kExactTailUnits)
+    {
+      /* a handful of units (the one-call SDK functions): fetch the results first and bring back exactly the bytes
+       * each unit produced -- what lies behind *destLen in the caller's buffer is not touched, and nothing that an
+       * earlier call left in the device arena can travel to this caller */
+      ok = lzb_cuda_ok(cudaMemcpyAsync(s.h_results, s.d_results, sl.count * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results") &&
+           lzb_cuda_ok(cudaStreamSynchronize(s.stream), "decode slice");
+      for (size_t j = 0; j < sl.count && ok; j++)
+      {
+        const LzbUnit &u = units[sl.first + j];
+        const size_t made = std::min<size_t>(s.h_results[j].dst_done, u.dst_cap);
+        if (made) ok = lzb_cuda_ok(cudaMemcpyAsync(out + u.dst_off, s.d_out + (u.dst_off - sl.dst_lo), made, cudaMemcpyDeviceToHost, s.stream), "D2H output");
+      }
+      if (!ok) { ret = SZ_ERROR_FAIL; break; }
+      pending_slot[si] = (int)k;
+      continue;
+    }
+    /* D2H: one copy per maximal run of units whose outputs tile the arena (never touch the gaps).  Batches copy whole
+     * capacities: waiting for the results first would serialise the download behind the kernel */
     size_t j = 0;
     while (j < sl.count && ok)
     {
@@ -549,12 +577,26 @@ SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte 
                     const LzbUnit *post_a, LzbResult *res_a, size_t n_a,
                     const LzbUnit *post_b, LzbResult *res_b, size_t n_b)
 {
+  if (devOutBytes < outBytes) devOutBytes = outBytes;
+  /* everything below is indexed by offsets that came out of an archive: nothing may leave the two device arenas */
+  {
+    auto inside = [](uint64_t off, uint64_t len, uint64_t arena) { return len <= arena && off <= arena - len; };
+    bool ok = true;
+    for (size_t i = 0; ok && i < n_copies; i++) ok = inside(copies[i].src_off, copies[i].len, packedBytes) && inside(copies[i].dst_off, copies[i].len, devOutBytes);
+    for (size_t i = 0; ok && i < n; i++) ok = inside(units[i].src_off, units[i].src_len, packedBytes) && inside(units[i].dst_off, units[i].dst_cap, devOutBytes);
+    for (size_t i = 0; ok && i < n_a; i++) ok = inside(post_a[i].dst_off, post_a[i].dst_cap, devOutBytes);
+    for (size_t i = 0; ok && i < n_b; i++) ok = inside(post_b[i].dst_off, post_b[i].dst_cap, devOutBytes);
+    for (size_t i = 0; ok && i < n_bcj2; i++)
+      ok = inside(bcj2[i].main_off, bcj2[i].main_size, devOutBytes) && inside(bcj2[i].call_off, bcj2[i].call_size, devOutBytes) &&
+           inside(bcj2[i].jump_off, bcj2[i].jump_size, devOutBytes) && inside(bcj2[i].out_off, bcj2[i].out_size, devOutBytes) &&
+           inside(bcj2[i].rc_off, bcj2[i].rc_size, packedBytes);
+    if (!ok) { lzb_set_error("a range of the job lies outside its arena"); return SZ_ERROR_FAIL; }
+  }
   std::lock_guard<std::mutex> g(c->mu);
   if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
   LzbSlot &s = c->slot[0];
   const ModelBytes model = model_bytes_for(units, n);
   const size_t most = std::max(n, std::max(n_a, n_b));
-  if (devOutBytes < outBytes) devOutBytes = outBytes;
   const size_t jobs_at = (packedBytes + 16 + 15) & ~(size_t)15;             /* the BCJ2 job table rides behind the archive */
   if (!lzb_slot_reserve(c, s, jobs_at + n_bcj2 * sizeof(LzbBcj2Job) + 16, devOutBytes + 16, most ? most : 1, n ? slab_bytes_for(model) : 0)) return SZ_ERROR_MEM;
   bool ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_packed, packed, packedBytes, cudaMemcpyHostToDevice, s.stream), "H2D archive");
@@ -591,12 +633,6 @@ SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte 
   if (outBytes && !lzb_cuda_ok(cudaMemcpyAsync(out, s.d_out, outBytes, cudaMemcpyDeviceToHost, s.stream), "D2H output")) return SZ_ERROR_FAIL;
   if (!lzb_cuda_ok(cudaStreamSynchronize(s.stream), "7z passes")) return SZ_ERROR_FAIL;
   return SZ_OK;
-}
-
-SRes lzb_decode_host_simple(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
-                            const LzbUnit *units, LzbResult *results, size_t n)
-{
-  return Lzb_DecodeUnitsHost(c, packed, packedBytes, out, outBytes, units, results, n);
 }
 
 /* ------------------------------------------------------------------ props ------------------- */

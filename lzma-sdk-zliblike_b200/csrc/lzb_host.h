@@ -34,6 +34,8 @@ struct LzbContext
   uint32_t *d_dev_tickets = nullptr;
   unsigned dev_seq = 0;
   uint8_t *d_dev_slab = nullptr; size_t dev_slab_cap = 0;
+  cudaEvent_t dev_event = nullptr;  /* recorded behind the last device-resident launch (they are ordered, lzb_host.cu) */
+  cudaStream_t dev_last_stream = nullptr;
   /* streamed launch (LzbFlow): device flags/counters, mapped host flags, a pinned constant, an event */
   uint32_t *d_flow = nullptr; uint32_t *h_flow = nullptr; uint32_t *h_flow_dev = nullptr; size_t flow_cap = 0;
   uint32_t *h_one = nullptr;
@@ -46,10 +48,6 @@ void lzb_set_error(const char *fmt, ...);
 bool lzb_cuda_ok(cudaError_t e, const char *what);
 LzbContext *lzb_default_context();                 /* lazily created; NULL (+ error text) without a GPU */
 bool lzb_slot_reserve(LzbContext *c, LzbSlot &s, size_t packed, size_t out, size_t units, size_t slab);
-
-/* run units through the fused kernel from host arenas (single slice, synchronous) */
-SRes lzb_decode_host_simple(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
-                            const LzbUnit *units, LzbResult *results, size_t n);
 
 struct LzbCopyRange { uint64_t src_off, dst_off, len; };
 /* devOutBytes >= outBytes: size of the device output arena (scratch streams may live behind the part that is

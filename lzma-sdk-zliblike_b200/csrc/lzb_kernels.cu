@@ -40,7 +40,7 @@ namespace lzb {
 constexpr uint32_t max_warps_for(uint32_t G) { return G == 32 ? 16u : (G == 16 ? 18u : 8u); }
 
 /* ---- a launch that is fed and drained while it runs (LzbFlow, lzb_kernels.h) ---- */
-constexpr long long kFlowTimeoutCycles = 8000000000ll;         /* ~4 s at 2 GHz */
+constexpr long long kFlowTimeoutCycles = 8000000000ll;         /* ~4 s at the B200's 1.97 GHz */
 
 /* wait until unit i's packed bytes (and the chunk after them: a 32-byte sector may straddle the boundary, and
  * L1 must never see a sector before all of it has landed) are in device memory; false = give up */
@@ -93,7 +93,7 @@ template <uint32_t G> __device__ __forceinline__ void flow_done(const LzbFlow &f
   Grp::sync();
 }
 
-template <bool kSharedModel, uint32_t G, bool kFlow>
+template <bool kSharedModel, uint32_t G, bool kFlow, bool kAhead>
 __global__ void __launch_bounds__(max_warps_for(G) * 32, 1)
 lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict__ out,
                         const LzbUnit *__restrict__ units, LzbResult *__restrict__ results, uint32_t n_units,
@@ -118,7 +118,7 @@ lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict_
   if (kSharedModel && G == 32 && smem_stride > region_bytes) matched_at = region + region_bytes;
   uint16_t *matched = reinterpret_cast<uint16_t *>(matched_at);
 
-  UnitDecoderT<G> d;
+  UnitDecoderT<G, kSharedModel, kAhead> d;
   LzbUnit u;
   uint32_t ui = 0;
   uint8_t *dst = out;
@@ -149,7 +149,7 @@ lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict_
         dst = out + u.dst_off;
         const bool stateful = (u.flags & LZB_UNIT_STATEFUL) != 0;
         d.begin(packed + u.src_off, u.src_len, dst, stateful ? u.filter_param : u.dst_cap, u.dict_size,
-                reinterpret_cast<uint16_t *>(region), matched, kSharedModel);
+                reinterpret_cast<uint16_t *>(region), matched);
         d.start_unit(u, stateful ? reinterpret_cast<LzbStreamState *>(u.expect) : nullptr);
       }
     }
@@ -193,82 +193,104 @@ lzb_post_only_kernel(uint8_t *__restrict__ data, const LzbUnit *__restrict__ uni
   if (lane == 0) results[i] = r;
 }
 
-/* BCJ2 (Bcj2.c:28-127): x86 branch targets were moved to two side streams (CALL: E8; JUMP: E9 and 0F 8x), one
- * adaptive bit per candidate (its own little range coder: 256 contexts for E8 by the previous byte, one for E9,
- * one for Jcc) says whether a candidate was moved.  The merge is one serial chain over the whole folder -- one
- * thread per folder; the folders of an archive are independent jobs. */
-__global__ void __launch_bounds__(32)
+/* BCJ2 merge (what the reference's Bcj2_Decode computes, Bcj2.c:28-127).  The encoder moved the absolute targets of
+ * x86 CALLs (E8) and of JMP / Jcc (E9, 0F 8x) out of the main stream into two side streams, big-endian, and coded one
+ * adaptive bit per opcode candidate -- 256 models for E8 (chosen by the byte before it), one for E9, one for Jcc --
+ * with a range coder into a fourth stream: bit 1 = "the four bytes after this opcode come from the side stream".
+ *
+ * One WARP per folder.  The merge is a serial chain only from candidate to candidate; between two candidates the main
+ * stream is plain bytes, and that is where the time goes, so the warp looks at 32 bytes at once: every lane tests
+ * its byte (with its left neighbour's byte for the 0F 8x form), a ballot finds the first candidate, and the bytes up
+ * to and including it are copied by the lanes in one coalesced step.  The bit models live in shared memory; every
+ * lane carries the coder's scalars redundantly.  Main stream and output share memory (the main stream sits at the
+ * end of the output range, 7zDec.c:408-430): a batch is loaded completely before it is stored and the output never
+ * overtakes the input, so the in-place merge is safe front to back. */
+namespace {
+constexpr uint32_t kBcj2Warps = 4;
+constexpr uint32_t kBcj2Models = 2 + 256;
+}
+
+__global__ void __launch_bounds__(kBcj2Warps * 32)
 lzb_bcj2_kernel(const uint8_t *__restrict__ packed, uint8_t *out_arena, LzbBcj2Job *jobs, uint32_t n_jobs)
 {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint16_t models[kBcj2Warps][kBcj2Models + 2];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t j = blockIdx.x * kBcj2Warps + warp;
   if (j >= n_jobs) return;
-  LzbBcj2Job job = jobs[j];
-  const uint8_t *main_s = out_arena + job.main_off, *call_s = out_arena + job.call_off, *jump_s = out_arena + job.jump_off;
+  const LzbBcj2Job job = jobs[j];
+  const uint8_t *main_s = out_arena + job.main_off;
+  const uint8_t *side[2] = { out_arena + job.call_off, out_arena + job.jump_off };
+  uint32_t side_left[2] = { job.call_size, job.jump_size };
   const uint8_t *rc = packed + job.rc_off;
   uint8_t *out = out_arena + job.out_off;
-  uint16_t p[258];
-  for (int i = 0; i < 258; i++) p[i] = 1024;
-  uint32_t rc_pos = 0, range = 0xFFFFFFFFu, code = 0;
-  int res = LZB_SZ_OK;
-  for (int i = 0; i < 5; i++)
+  uint16_t *model = models[warp];
+  for (uint32_t i = lane; i < kBcj2Models; i += 32) model[i] = 1024;
+  __syncwarp();
+
+  /* range coder start: five bytes, the first ends up shifted out */
+  uint32_t range = 0xFFFFFFFFu, code = 0, rc_at = 0;
+  bool broken = job.rc_size < 5;
+  if (!broken) for (; rc_at < 5; rc_at++) code = (code << 8) | rc[rc_at];
+
+  uint32_t in_at = 0, out_at = 0, prev = 0;
+  while (!broken && out_at < job.out_size)
   {
-    if (rc_pos == job.rc_size) { res = LZB_SZ_ERROR_DATA; break; }
-    code = (code << 8) | rc[rc_pos++];
-  }
-  uint32_t in_pos = 0, out_pos = 0, call_pos = 0, jump_pos = 0;
-  uint8_t prev = 0;
-  if (res == LZB_SZ_OK && job.out_size != 0)
-  {
-    for (;;)
+    /* plain run: copy up to and including the next opcode candidate */
+    uint32_t budget = min(job.main_size - in_at, job.out_size - out_at);
+    bool at_candidate = false;
+    while (budget != 0 && !at_candidate)
     {
-      /* plain bytes up to and including the next branch opcode */
-      uint32_t limit = job.main_size - in_pos;
-      if (job.out_size - out_pos < limit) limit = job.out_size - out_pos;
-      while (limit != 0)
-      {
-        const uint8_t b = main_s[in_pos];
-        out[out_pos++] = b;
-        if ((b & 0xFE) == 0xE8 || (prev == 0x0F && (b & 0xF0) == 0x80)) break;
-        in_pos++;
-        prev = b;
-        limit--;
-      }
-      if (limit == 0 || out_pos == job.out_size) break;
-      const uint8_t b = main_s[in_pos++];
-      uint16_t *pr = b == 0xE8 ? p + prev : (b == 0xE9 ? p + 256 : p + 257);
-      const uint32_t t = *pr, bound = (range >> 11) * t;
-      bool moved;
-      if (code < bound) { range = bound; *pr = (uint16_t)(t + ((2048 - t) >> 5)); moved = false; }
-      else { range -= bound; code -= bound; *pr = (uint16_t)(t - (t >> 5)); moved = true; }
-      if (range < (1u << 24))
-      {
-        if (rc_pos == job.rc_size) { res = LZB_SZ_ERROR_DATA; break; }
-        range <<= 8; code = (code << 8) | rc[rc_pos++];
-      }
-      if (!moved) { prev = b; continue; }
-      const uint8_t *v;
-      if (b == 0xE8)
-      {
-        if (job.call_size - call_pos < 4) { res = LZB_SZ_ERROR_DATA; break; }
-        v = call_s + call_pos; call_pos += 4;
-      }
-      else
-      {
-        if (job.jump_size - jump_pos < 4) { res = LZB_SZ_ERROR_DATA; break; }
-        v = jump_s + jump_pos; jump_pos += 4;
-      }
-      const uint32_t dest = (((uint32_t)v[0] << 24) | ((uint32_t)v[1] << 16) | ((uint32_t)v[2] << 8) | v[3]) - (out_pos + 4);
-      out[out_pos++] = (uint8_t)dest;
-      if (out_pos == job.out_size) break;
-      out[out_pos++] = (uint8_t)(dest >> 8);
-      if (out_pos == job.out_size) break;
-      out[out_pos++] = (uint8_t)(dest >> 16);
-      if (out_pos == job.out_size) break;
-      out[out_pos++] = prev = (uint8_t)(dest >> 24);
+      /* (a damaged folder can make the output overtake the main stream it shares memory with: then the reference's
+       * byte-by-byte order is what defines the bytes, one at a time) */
+      const uint32_t n = (out + out_at > main_s + in_at) ? 1u : min(budget, 32u);
+      const uint32_t b = lane < n ? main_s[in_at + lane] : 0u;
+      uint32_t left = __shfl_up_sync(0xffffffffu, b, 1);
+      if (lane == 0) left = prev;
+      const bool cand = lane < n && ((b & 0xFEu) == 0xE8u || (left == 0x0Fu && (b & 0xF0u) == 0x80u));
+      const uint32_t hits = __ballot_sync(0xffffffffu, cand);
+      const uint32_t plain = hits ? (uint32_t)__ffs((int)hits) - 1u : n;      /* bytes before the candidate */
+      const uint32_t copy = hits ? plain + 1u : n;
+      __syncwarp();                                       /* the whole batch is in registers before any byte of it is stored */
+      if (lane < copy) out[out_at + lane] = (uint8_t)b;
+      if (plain != 0) prev = __shfl_sync(0xffffffffu, b, (int)plain - 1);
+      in_at += plain; out_at += copy; budget -= plain;
+      at_candidate = hits != 0;
+      __syncwarp();
     }
-    if (res == LZB_SZ_OK && out_pos != job.out_size) res = LZB_SZ_ERROR_DATA;
+    if (!at_candidate || out_at == job.out_size) break;
+
+    /* the candidate's bit */
+    const uint32_t op = main_s[in_at++];
+    uint16_t *m = model + (op == 0xE8u ? prev : (op == 0xE9u ? 256u : 257u));
+    const uint32_t pr = *m;
+    const uint32_t bound = (range >> 11) * pr;
+    const bool moved = code >= bound;
+    __syncwarp();
+    if (moved) { range -= bound; code -= bound; *m = (uint16_t)(pr - (pr >> 5)); }
+    else { range = bound; *m = (uint16_t)(pr + ((2048u - pr) >> 5)); }
+    __syncwarp();
+    if (range < (1u << 24))
+    {
+      if (rc_at == job.rc_size) { broken = true; break; }
+      range <<= 8;
+      code = (code << 8) | rc[rc_at++];
+    }
+    if (!moved) { prev = op; continue; }
+
+    /* four bytes of absolute target from the side stream -> relative displacement */
+    const uint32_t which = op == 0xE8u ? 0u : 1u;
+    if (side_left[which] < 4) { broken = true; break; }
+    const uint8_t *v = side[which];
+    side[which] += 4; side_left[which] -= 4;
+    const uint32_t target = ((uint32_t)v[0] << 24) | ((uint32_t)v[1] << 16) | ((uint32_t)v[2] << 8) | v[3];
+    const uint32_t rel = target - (out_at + 4);
+    const uint32_t room = min(4u, job.out_size - out_at);
+    if (lane < room) out[out_at + lane] = (uint8_t)(rel >> (8 * lane));
+    out_at += room;
+    prev = rel >> 24;
+    __syncwarp();
   }
-  jobs[j].res = res;
+  if (lane == 0) jobs[j].res = (!broken && out_at == job.out_size) ? LZB_SZ_OK : LZB_SZ_ERROR_DATA;
 }
 
 /* xz block check 10 (SHA-256, Xz.c:45-88): a digest is one serial chain, so one thread per job; blocks of
@@ -296,6 +318,7 @@ static uint32_t env_u32(const char *name, uint32_t dflt)
 }
 
 static int g_dev_sms = 0;
+static uint32_t g_ahead_max_warps = 8;      /* LZB_AHEAD_WARPS overrides (0 = never), read once */
 static size_t g_dev_smem_optin = 0;
 
 static cudaError_t query_device()
@@ -310,6 +333,7 @@ static cudaError_t query_device()
   if (e != cudaSuccess) return e;
   g_dev_sms = sms;
   g_dev_smem_optin = (size_t)smem;
+  if (const char *v = getenv("LZB_AHEAD_WARPS")) g_ahead_max_warps = (uint32_t)atoi(v);
   return cudaSuccess;
 }
 
@@ -328,10 +352,11 @@ extern "C" int lzb_launch_geometry(uint32_t smem_model_bytes, uint32_t gmem_mode
   g->ctas = (uint32_t)g_dev_sms;
   /* lanes per unit (LZB_GROUP = 32, 16, 8 or 4) and units per SM (LZB_UNITS), both overridable for
    * measurements; defaults from profiles/r01_c_residency.md */
-  uint32_t G = env_u32("LZB_GROUP", LZB_DEFAULT_GROUP);
+  static const uint32_t env_group = env_u32("LZB_GROUP", LZB_DEFAULT_GROUP), env_units = env_u32("LZB_UNITS", LZB_DEFAULT_UNITS_PER_SM);
+  uint32_t G = env_group;
   if (G != 32 && G != 16 && G != 8 && G != 4) G = LZB_DEFAULT_GROUP;
   const uint32_t K = 32 / G;
-  uint32_t want_units = env_u32("LZB_UNITS", LZB_DEFAULT_UNITS_PER_SM);
+  uint32_t want_units = env_units;
   if (region <= LZB_MAX_SHARED_MODEL_BYTES)
   {
     uint32_t units = (uint32_t)(g_dev_smem_optin / region);
@@ -356,6 +381,7 @@ extern "C" int lzb_launch_geometry(uint32_t smem_model_bytes, uint32_t gmem_mode
     g->slab_stride = region + gpart;
   }
   g->group = G;
+  g->ahead = 0;
   g->units_per_cta = g->warps_per_cta * (32 / G);
   g->slab_bytes = (size_t)g->slab_stride * g->units_per_cta * g->ctas;
   return 0;
@@ -394,23 +420,39 @@ extern "C" void lzb_plan_few_units(LzbGeometry *gp, uint32_t n_units, size_t sme
     const uint32_t full = g.region_bytes + g.slab_stride;
     if (g.warps_per_cta <= (uint32_t)(smem_optin / full)) g.smem_stride = full;
   }
+  /* With at most kAheadMaxWarps units on an SM the issue slots are mostly idle and a unit is bound by its own
+   * dependency chain: the look-ahead form of the decoder (predicated normalisation, both children of a tree node
+   * loaded while the bit is decided; lzb_core.cuh) trades ~25 % more issued instructions for a shorter chain.
+   * Above that the issue slots are the bound again and the lean form wins (profiles/r02_b_*). */
+  g.ahead = (g.shared_model && g.group == 32 && g.warps_per_cta <= g_ahead_max_warps) ? 1 : 0;
 }
 
-template <bool kShared, uint32_t G, bool kFlow>
-static cudaError_t launch_variant2(const LzbGeometry &g, uint32_t ctas, const uint8_t *d_packed, uint8_t *d_out,
+template <bool kShared, uint32_t G, bool kFlow, bool kAhead>
+static cudaError_t launch_variant3(const LzbGeometry &g, uint32_t ctas, const uint8_t *d_packed, uint8_t *d_out,
                                   const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units, uint32_t *d_ticket,
                                   uint8_t *d_slab, const LzbFlow &flow, cudaStream_t stream)
 {
   const size_t smem = kShared ? (size_t)g.units_per_cta * g.smem_stride : 0;
   if (kShared)
   {
-    cudaError_t e = cudaFuncSetAttribute(lzb::lzb_decode_units_kernel<kShared, G, kFlow>,
+    cudaError_t e = cudaFuncSetAttribute(lzb::lzb_decode_units_kernel<kShared, G, kFlow, kAhead>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  lzb::lzb_decode_units_kernel<kShared, G, kFlow><<<ctas, g.warps_per_cta * 32, smem, stream>>>(
+  lzb::lzb_decode_units_kernel<kShared, G, kFlow, kAhead><<<ctas, g.warps_per_cta * 32, smem, stream>>>(
       d_packed, d_out, d_units, d_results, n_units, d_ticket, g.region_bytes, g.smem_stride, g.slab_stride, d_slab, flow);
   return cudaGetLastError();
+}
+
+/* the look-ahead form of the decoder exists for one-unit-per-warp launches with the model in shared memory only */
+template <bool kShared, uint32_t G, bool kFlow>
+static cudaError_t launch_variant2(const LzbGeometry &g, uint32_t ctas, const uint8_t *d_packed, uint8_t *d_out,
+                                  const LzbUnit *d_units, LzbResult *d_results, uint32_t n_units, uint32_t *d_ticket,
+                                  uint8_t *d_slab, const LzbFlow &flow, cudaStream_t stream)
+{
+  if (kShared && G == 32 && g.ahead)
+    return launch_variant3<kShared, G, kFlow, kShared && G == 32>(g, ctas, d_packed, d_out, d_units, d_results, n_units, d_ticket, d_slab, flow, stream);
+  return launch_variant3<kShared, G, kFlow, false>(g, ctas, d_packed, d_out, d_units, d_results, n_units, d_ticket, d_slab, flow, stream);
 }
 
 /* the streamed variant is a separate instantiation: the plain launch keeps its register allocation (the
@@ -446,8 +488,9 @@ extern "C" int lzb_launch_decode_flow(const uint8_t *d_packed, uint8_t *d_out, c
   if (rc) return rc;
   if (n_units == 0) return 0;
   if (!d_model_slab) return (int)cudaErrorInvalidValue;
-  lzb_plan_few_units(&g, n_units, g_dev_smem_optin, getenv("LZB_GROUP") == nullptr,
-                     getenv("LZB_SMEM_MATCHED") != nullptr && atoi(getenv("LZB_SMEM_MATCHED")) == 0);
+  static const bool group_forced = getenv("LZB_GROUP") != nullptr;
+  static const bool dense = getenv("LZB_SMEM_MATCHED") != nullptr && atoi(getenv("LZB_SMEM_MATCHED")) == 0;
+  lzb_plan_few_units(&g, n_units, g_dev_smem_optin, !group_forced, dense);
   uint32_t ctas = g.ctas;
   if ((uint64_t)ctas * g.units_per_cta > n_units) ctas = (n_units + g.units_per_cta - 1) / g.units_per_cta;
   cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t), stream);
@@ -481,6 +524,6 @@ extern "C" int lzb_launch_sha256(const uint8_t *d_data, LzbShaJob *d_jobs, uint3
 extern "C" int lzb_launch_bcj2(const uint8_t *d_packed, uint8_t *d_out, LzbBcj2Job *d_jobs, uint32_t n_jobs, cudaStream_t stream)
 {
   if (n_jobs == 0) return 0;
-  lzb::lzb_bcj2_kernel<<<(n_jobs + 31) / 32, 32, 0, stream>>>(d_packed, d_out, d_jobs, n_jobs);
+  lzb::lzb_bcj2_kernel<<<(n_jobs + 3) / 4, 128, 0, stream>>>(d_packed, d_out, d_jobs, n_jobs);
   return (int)cudaGetLastError();
 }

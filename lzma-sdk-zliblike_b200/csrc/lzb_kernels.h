@@ -27,6 +27,7 @@ typedef struct LzbGeometry
                                one-unit-per-warp launch keeps the matched-literal trees in shared memory too */
   uint32_t slab_stride;     /* HBM slab bytes per unit (matched-literal trees, or the whole model) */
   int shared_model;
+  int ahead;                /* one-unit-per-warp launch with few enough warps per SM: look-ahead form of the decoder */
   size_t slab_bytes;        /* slab the caller must provide: ctas * units_per_cta * slab_stride */
 } LzbGeometry;
 

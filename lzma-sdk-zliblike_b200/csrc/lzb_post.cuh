@@ -393,8 +393,9 @@ LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t 
   const uint32_t n = r.dst_done;
   if (u.filter == LZB_FILTER_X86)
   {
-    /* stand-alone x86_Convert calls pass the direction in flags bit 1 and the history in `expect` */
-    uint32_t st = (uint32_t)(u.expect >> 32) & 7;
+    /* stand-alone x86_Convert calls pass the direction in flags bit 1 and the history in `expect`; a filter fused
+     * behind a decode starts a block / folder with no history (`expect` is the stored digest there) */
+    uint32_t st = (u.flags & LZB_UNIT_POST_REPORT) ? ((uint32_t)(u.expect >> 32) & 7) : 0u;
     const uint32_t done = x86_convert_group<G>(data, n, u.filter_param, (u.flags & 2) != 0, st);
     if (u.flags & 4) { r.src_used = done; r.status = (int32_t)st; }   /* stand-alone call: report them */
   }

@@ -142,114 +142,135 @@ extern "C" int XzCheck_Final(CXzCheck *p, Byte *digest)
 }
 
 /* ------------------------------------------------------------------ BCJ / Delta stage ----------- */
-/* Staging buffer: [0, handed) already given to the caller, [handed, converted) filtered and waiting,
- * [converted, held) raw bytes the filter could not finish yet (an x86 candidate needs 5 bytes). */
-struct BraStage
+/* An xz branch / delta filter (xz format 5.3; reference object: BraState, XzDec.c:48-232) works in place on a
+ * 16 KiB WINDOW of the stream that flows through it.  The window is three runs of bytes, front to back:
+ *
+ *      [ taken | ripe | raw ]        taken : already handed to the next stage
+ *        0   t_end  r_end  fill      ripe  : filtered, waiting to be handed on
+ *                                    raw   : not filtered yet (a converter stops short of the end of what it is
+ *                                            given: an x86 candidate needs 5 bytes, ARM/PPC/SPARC 4, IA64 16)
+ *
+ * One call alternates "hand ripe bytes on" and "slide, refill from the input, filter" until the output is full or
+ * nothing moves.  The window size and this order are what fix how many bytes each call consumes and produces
+ * -- which a caller of XzUnpacker_Code can observe -- so they are kept; the converters run on the GPU. */
+struct FilterStage
 {
-  size_t handed, converted, held;
+  size_t t_end, r_end, fill;
   UInt32 method;
   int encode;
   UInt32 delta, ip, x86_state;
   Byte delta_state[DELTA_STATE_SIZE];
-  Byte buf[LZB_BRA_BUF_SIZE];
+  Byte win[LZB_BRA_BUF_SIZE];
 };
 
-static void bra_free(void *pp, ISzAlloc *alloc) { alloc->Free(alloc, pp); }
-
-static SRes bra_set_props(void *pp, const Byte *props, size_t propSize, ISzAlloc *alloc)
+/* what the filter ids of the xz format ask for: start-offset alignment and the converter behind it */
+typedef size_t (*FilterRun)(FilterStage *f, Byte *data, size_t n);
+static size_t run_delta(FilterStage *f, Byte *d, size_t n)
 {
-  /* XzDec.c:71-110 for the two methods this library runs */
-  BraStage *b = (BraStage *)pp;
-  (void)alloc;
-  b->encode = 0;
-  b->ip = 0;
-  if (b->method == XZ_ID_Delta)
+  if (f->encode) Delta_Encode(f->delta_state, f->delta, d, n); else Delta_Decode(f->delta_state, f->delta, d, n);
+  return n;
+}
+static size_t run_x86(FilterStage *f, Byte *d, size_t n) { return x86_Convert(d, n, f->ip, &f->x86_state, f->encode); }
+static size_t run_ppc(FilterStage *f, Byte *d, size_t n) { return PPC_Convert(d, n, f->ip, f->encode); }
+static size_t run_ia64(FilterStage *f, Byte *d, size_t n) { return IA64_Convert(d, n, f->ip, f->encode); }
+static size_t run_arm(FilterStage *f, Byte *d, size_t n) { return ARM_Convert(d, n, f->ip, f->encode); }
+static size_t run_armt(FilterStage *f, Byte *d, size_t n) { return ARMT_Convert(d, n, f->ip, f->encode); }
+static size_t run_sparc(FilterStage *f, Byte *d, size_t n) { return SPARC_Convert(d, n, f->ip, f->encode); }
+
+static const struct FilterKind { UInt32 id; UInt32 offset_mask; FilterRun run; } k_filter_kinds[] =
+{
+  { XZ_ID_Delta, 0, run_delta }, { XZ_ID_X86, 0, run_x86 },   { XZ_ID_PPC, 3, run_ppc },     { XZ_ID_IA64, 15, run_ia64 },
+  { XZ_ID_ARM, 3, run_arm },     { XZ_ID_ARMT, 1, run_armt }, { XZ_ID_SPARC, 3, run_sparc },
+};
+
+static const FilterKind *filter_kind(UInt64 id)
+{
+  for (const FilterKind &k : k_filter_kinds) if (k.id == id) return &k;
+  return nullptr;
+}
+
+static void stage_release(void *pp, ISzAlloc *alloc) { alloc->Free(alloc, pp); }
+
+/* filter properties (xz format 5.3.1 / 5.3.2): Delta = one byte "distance - 1"; a branch converter = nothing, or a
+ * 32-bit start offset that must respect the instruction alignment of its architecture */
+static SRes stage_props(void *pp, const Byte *props, size_t n, ISzAlloc *)
+{
+  FilterStage *f = (FilterStage *)pp;
+  const FilterKind *kind = filter_kind(f->method);
+  f->encode = 0;
+  f->ip = 0;
+  if (f->method == XZ_ID_Delta)
   {
-    if (propSize != 1) return SZ_ERROR_UNSUPPORTED;
-    b->delta = (UInt32)props[0] + 1;
+    if (n != 1) return SZ_ERROR_UNSUPPORTED;
+    f->delta = 1u + props[0];
     return SZ_OK;
   }
-  if (propSize == 4)
-  {
-    const UInt32 v = lzb_le32(props);
-    const UInt32 need = b->method == XZ_ID_X86 ? 0u : (b->method == XZ_ID_IA64 ? 15u : (b->method == XZ_ID_ARMT ? 1u : 3u));
-    if (v & need) return SZ_ERROR_UNSUPPORTED;
-    b->ip = v;
-  }
-  else if (propSize != 0) return SZ_ERROR_UNSUPPORTED;
+  if (n == 0) return SZ_OK;
+  if (n != 4 || !kind) return SZ_ERROR_UNSUPPORTED;
+  const UInt32 start = lzb_le32(props);
+  if (start & kind->offset_mask) return SZ_ERROR_UNSUPPORTED;
+  f->ip = start;
   return SZ_OK;
 }
 
-static void bra_init(void *pp)
+static void stage_reset(void *pp)
 {
-  BraStage *b = (BraStage *)pp;
-  b->handed = b->converted = b->held = 0;
-  b->x86_state = 0;
-  if (b->method == XZ_ID_Delta) Delta_Init(b->delta_state);
+  FilterStage *f = (FilterStage *)pp;
+  f->t_end = f->r_end = f->fill = 0;
+  f->x86_state = 0;
+  if (f->method == XZ_ID_Delta) Delta_Init(f->delta_state);
 }
 
-/* XzDec.c:124-196 */
-static SRes bra_code(void *pp, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen, int srcWasFinished,
-                     ECoderFinishMode finishMode, int *wasFinished)
+static SRes stage_code(void *pp, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen, int srcWasFinished,
+                       ECoderFinishMode, int *wasFinished)
 {
-  BraStage *b = (BraStage *)pp;
-  size_t room = *destLen, avail = *srcLen;
-  (void)finishMode;
-  *destLen = 0; *srcLen = 0; *wasFinished = 0;
-  while (room != 0)
+  FilterStage *f = (FilterStage *)pp;
+  const FilterKind *kind = filter_kind(f->method);
+  Byte *out = dest, *const out_end = dest + *destLen;
+  const Byte *in = src, *const in_end = src + *srcLen;
+  *wasFinished = 0;
+  while (out != out_end)
   {
-    if (b->handed != b->converted)
+    if (f->t_end != f->r_end)
     {
-      const size_t n = std::min(b->converted - b->handed, room);
-      memcpy(dest, b->buf + b->handed, n);
-      b->handed += n; dest += n; room -= n; *destLen += n;
+      /* hand ripe bytes on */
+      const size_t n = std::min<size_t>(f->r_end - f->t_end, (size_t)(out_end - out));
+      memcpy(out, f->win + f->t_end, n);
+      out += n; f->t_end += n;
       continue;
     }
-    /* nothing converted is waiting: drop what was handed out, top the buffer up, filter again */
-    b->held -= b->handed;
-    memmove(b->buf, b->buf + b->handed, b->held);
-    b->handed = b->converted = 0;
+    /* slide what is still raw to the front, refill, filter */
+    f->fill -= f->t_end;
+    memmove(f->win, f->win + f->t_end, f->fill);
+    f->t_end = f->r_end = 0;
+    const size_t n = std::min<size_t>(LZB_BRA_BUF_SIZE - f->fill, (size_t)(in_end - in));
+    memcpy(f->win + f->fill, in, n);
+    in += n; f->fill += n;
+    if (f->fill == 0) break;
+    if (!kind) { *destLen = (SizeT)(out - dest); *srcLen = (SizeT)(in - src); return SZ_ERROR_UNSUPPORTED; }
+    f->r_end = kind->run(f, f->win, f->fill);
+    f->ip += (UInt32)f->r_end;
+    if (f->r_end == 0)
     {
-      const size_t n = std::min(LZB_BRA_BUF_SIZE - b->held, avail);
-      memcpy(b->buf + b->held, src, n);
-      b->held += n; src += n; avail -= n; *srcLen += n;
-    }
-    if (b->held == 0) break;
-    if (b->method == XZ_ID_Delta)
-    {
-      if (b->encode) Delta_Encode(b->delta_state, b->delta, b->buf, b->held);
-      else Delta_Decode(b->delta_state, b->delta, b->buf, b->held);
-      b->converted = b->held;
-    }
-    else if (b->method == XZ_ID_X86) b->converted = x86_Convert(b->buf, b->held, b->ip, &b->x86_state, b->encode);
-    else if (b->method == XZ_ID_PPC) b->converted = PPC_Convert(b->buf, b->held, b->ip, b->encode);
-    else if (b->method == XZ_ID_IA64) b->converted = IA64_Convert(b->buf, b->held, b->ip, b->encode);
-    else if (b->method == XZ_ID_ARM) b->converted = ARM_Convert(b->buf, b->held, b->ip, b->encode);
-    else if (b->method == XZ_ID_ARMT) b->converted = ARMT_Convert(b->buf, b->held, b->ip, b->encode);
-    else if (b->method == XZ_ID_SPARC) b->converted = SPARC_Convert(b->buf, b->held, b->ip, b->encode);
-    else
-      return SZ_ERROR_UNSUPPORTED;
-    b->ip += (UInt32)b->converted;
-    if (b->converted == 0)
-    {
-      if (!srcWasFinished) break;          /* the tail may still grow into a convertible instruction */
-      b->converted = b->held;              /* end of data: the last bytes pass unfiltered (XzDec.c:186-191) */
+      if (!srcWasFinished) break;         /* the raw tail may still grow into something convertible */
+      f->r_end = f->fill;                 /* end of the data: the last bytes pass as they are */
     }
   }
-  if (b->held == b->handed && avail == 0 && srcWasFinished) *wasFinished = 1;
+  *destLen = (SizeT)(out - dest);
+  *srcLen = (SizeT)(in - src);
+  if (srcWasFinished && in == in_end && f->t_end == f->fill) *wasFinished = 1;
   return SZ_OK;
 }
 
-static SRes bra_attach(IStateCoder *sc, UInt64 id, ISzAlloc *alloc)
+static SRes stage_attach(IStateCoder *sc, UInt64 id, ISzAlloc *alloc)
 {
-  /* XzDec.c:198-221 */
-  if (id != XZ_ID_Delta && (id < XZ_ID_X86 || id > XZ_ID_SPARC)) return SZ_ERROR_UNSUPPORTED;
   sc->p = 0;
-  BraStage *b = (BraStage *)alloc->Alloc(alloc, sizeof(BraStage));
-  if (!b) return SZ_ERROR_MEM;
-  b->method = (UInt32)id;
-  sc->p = b;
-  sc->Free = bra_free; sc->SetProps = bra_set_props; sc->Init = bra_init; sc->Code = bra_code;
+  if (!filter_kind(id)) return SZ_ERROR_UNSUPPORTED;
+  FilterStage *f = (FilterStage *)alloc->Alloc(alloc, sizeof(FilterStage));
+  if (!f) return SZ_ERROR_MEM;
+  f->method = (UInt32)id;
+  sc->p = f;
+  sc->Free = stage_release; sc->SetProps = stage_props; sc->Init = stage_reset; sc->Code = stage_code;
   return SZ_OK;
 }
 
@@ -321,72 +342,117 @@ extern "C" SRes MixCoder_SetFromMethod(CMixCoder *p, int coderIndex, UInt64 meth
   p->ids[coderIndex] = methodId;
   if (methodId == XZ_ID_LZMA2) return l2_attach(sc, p->alloc);
   if (coderIndex == 0) return SZ_ERROR_UNSUPPORTED;        /* a chain starts with a real decoder */
-  return bra_attach(sc, methodId, p->alloc);
+  return stage_attach(sc, methodId, p->alloc);
 }
 
-/* XzDec.c:375-480.  Stage i reads what stage i-1 left in its hand-over buffer and writes into its own
- * (or into dest for the last stage); rounds repeat until one makes no progress.
+/* The chain of a block (xz format 3.1.2: filters are listed in the order the ENCODER applied them; the decoder runs
+ * them backwards).  Reference object: CMixCoder, XzDec.c:356-480 -- its fields are ABI (include/lzb200.h).
+ *
+ * Neighbouring stages are joined by a hand-over buffer of 128 KiB: link j carries the bytes stage j has produced
+ * (size[j]), how many of them stage j+1 has taken (pos[j]) and whether stage j said it was finished.  A stage may
+ * write into its link only when the link is empty -- it always gets the whole buffer.  Rounds over the stages repeat
+ * until a whole round moves no byte.
  * observable: `status` is FINISHED_WITH_MARK only when EVERY stage call made during this invocation said
- * "finished" -- a chain that finishes in a later round of the same invocation still reports NOT_FINISHED
- * and is seen finished by the next invocation. */
+ * "finished" -- a chain that finishes in a later round of the same invocation still reports NOT_FINISHED and is
+ * seen finished by the next invocation. */
+namespace {
+
+struct ByteRun { const Byte *p; SizeT n; int ended; };          /* what a stage may read */
+struct ByteRoom { Byte *p; SizeT n; };                          /* where a stage may write */
+
+struct Chain
+{
+  CMixCoder *m;
+  const Byte *src; SizeT src_left; int src_ended;
+  Byte *dest; SizeT dest_left;
+
+  Byte *link(int j) const { return m->buf + LZB_CODER_BUF_SIZE * (size_t)j; }
+  int last() const { return m->numCoders - 1; }
+
+  ByteRun input_of(int i) const
+  {
+    if (i == 0) return { src, src_left, src_ended };
+    const int j = i - 1;
+    return { link(j) + m->pos[j], (SizeT)(m->size[j] - m->pos[j]), m->finished[j] };
+  }
+  /* false: the stage's link still holds bytes the next stage has not taken */
+  bool output_of(int i, ByteRoom &r) const
+  {
+    if (i == last()) { r = { dest, dest_left }; return true; }
+    if (m->pos[i] != m->size[i]) return false;
+    r = { link(i), (SizeT)LZB_CODER_BUF_SIZE };
+    return true;
+  }
+  void consumed(int i, SizeT n)
+  {
+    if (i == 0) { src += n; src_left -= n; }
+    else m->pos[i - 1] += n;
+  }
+  void produced(int i, SizeT n, int ended)
+  {
+    if (i == last()) { dest += n; dest_left -= n; }
+    else { m->size[i] = n; m->pos[i] = 0; m->finished[i] = ended; }
+  }
+};
+
+}  // namespace
+
 extern "C" SRes MixCoder_Code(CMixCoder *p, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen, int srcWasFinished,
                               ECoderFinishMode finishMode, ECoderStatus *status)
 {
-  const SizeT dest_cap = *destLen, src_avail = *srcLen;
-  bool all_said_finished = true;
-  *destLen = 0; *srcLen = 0;
+  Chain c = { p, src, *srcLen, srcWasFinished, dest, *destLen };
+  const SizeT src_all = *srcLen, dest_all = *destLen;
+  *srcLen = 0; *destLen = 0;
   *status = CODER_STATUS_NOT_FINISHED;
   if (!p->buf)
   {
     p->buf = (Byte *)p->alloc->Alloc(p->alloc, LZB_CODER_BUF_SIZE * (MIXCODER_NUM_FILTERS_MAX - 1));
     if (!p->buf) return SZ_ERROR_MEM;
   }
-  if (p->numCoders != 1) finishMode = CODER_FINISH_ANY;
-  const int last = p->numCoders - 1;
-  for (bool progress = true; progress;)
+  /* only a lone stage sees the caller's finish mode: inside a chain "the output is full" says nothing about the end */
+  const ECoderFinishMode mode = p->numCoders == 1 ? finishMode : CODER_FINISH_ANY;
+  int calls = 0, calls_finished = 0;
+  SRes res = SZ_OK;
+  for (bool moved = true; moved && res == SZ_OK;)
   {
-    progress = false;
-    for (int i = 0; i <= last; i++)
+    moved = false;
+    for (int i = 0; i <= c.last() && res == SZ_OK; i++)
     {
-      const Byte *in;
-      SizeT in_len, out_len;
-      Byte *out;
-      int in_finished, said_finished = 0;
-      if (i == 0) { in = src; in_len = src_avail - *srcLen; in_finished = srcWasFinished; }
-      else
-      {
-        in = p->buf + LZB_CODER_BUF_SIZE * (size_t)(i - 1) + p->pos[i - 1];
-        in_len = p->size[i - 1] - p->pos[i - 1];
-        in_finished = p->finished[i - 1];
-      }
-      if (i == last) { out = dest; out_len = dest_cap - *destLen; }
-      else
-      {
-        if (p->pos[i] != p->size[i]) continue;             /* the next stage has not drained it yet */
-        out = p->buf + LZB_CODER_BUF_SIZE * (size_t)i;
-        out_len = LZB_CODER_BUF_SIZE;
-      }
-      const SRes r = p->coders[i].Code(p->coders[i].p, out, &out_len, in, &in_len, in_finished, finishMode, &said_finished);
-      if (!said_finished) all_said_finished = false;
-      if (i == 0) { *srcLen += in_len; src += in_len; }
-      else p->pos[i - 1] += in_len;
-      if (i == last) { *destLen += out_len; dest += out_len; }
-      else { p->size[i] = out_len; p->pos[i] = 0; p->finished[i] = said_finished; }
-      if (r != SZ_OK) return r;
-      if (out_len != 0 || in_len != 0) progress = true;
+      ByteRoom room;
+      if (!c.output_of(i, room)) continue;
+      const ByteRun in = c.input_of(i);
+      SizeT took = in.n, made = room.n;
+      int ended = 0;
+      IStateCoder &st = p->coders[i];
+      res = st.Code(st.p, room.p, &made, in.p, &took, in.ended, mode, &ended);
+      calls++; calls_finished += ended ? 1 : 0;
+      c.consumed(i, took);
+      c.produced(i, made, ended);
+      if (took != 0 || made != 0) moved = true;
     }
   }
-  if (all_said_finished) *status = CODER_STATUS_FINISHED_WITH_MARK;
+  *srcLen = src_all - c.src_left;
+  *destLen = dest_all - c.dest_left;
+  if (res != SZ_OK) return res;
+  if (calls == calls_finished) *status = CODER_STATUS_FINISHED_WITH_MARK;
   return SZ_OK;
 }
 
-/* XzDec.c:558-588: filters are listed in encoding order, the chain runs them backwards */
+/* Bind the chain to a parsed block header (reference entry point: XzDec_Init, XzDec.c:558-588).  Stage i runs the
+ * block's filter n-1-i.  The stage objects are kept when the new block asks for the same methods in the same
+ * order, which is the normal case for every block of a stream after the first. */
+static bool chain_matches(const CMixCoder *p, const CXzBlock *block, int n)
+{
+  if (p->numCoders != n) return false;
+  for (int i = 0; i < n; i++)
+    if (p->ids[i] != block->filters[n - 1 - i].id) return false;
+  return true;
+}
+
 extern "C" SRes XzDec_Init(CMixCoder *p, const CXzBlock *block)
 {
   const int n = XzBlock_GetNumFilters(block);
-  bool same = n == p->numCoders;
-  for (int i = 0; same && i < n; i++) same = p->ids[i] == block->filters[n - 1 - i].id;
-  if (!same)
+  if (!chain_matches(p, block, n))
   {
     MixCoder_Free(p);
     p->numCoders = n;
@@ -398,9 +464,8 @@ extern "C" SRes XzDec_Init(CMixCoder *p, const CXzBlock *block)
   }
   for (int i = 0; i < n; i++)
   {
-    const CXzFilter *f = &block->filters[n - 1 - i];
-    IStateCoder *sc = &p->coders[i];
-    const SRes r = sc->SetProps(sc->p, f->props, f->propsSize, p->alloc);
+    const CXzFilter &f = block->filters[n - 1 - i];
+    const SRes r = p->coders[i].SetProps(p->coders[i].p, f.props, f.propsSize, p->alloc);
     if (r != SZ_OK) return r;
   }
   MixCoder_Init(p);
@@ -412,8 +477,6 @@ extern "C" SRes XzDec_Init(CMixCoder *p, const CXzBlock *block)
  * there: the payload of the block is complete (decoded ahead), the chain's "finished" has not been
  * delivered to the caller yet (see MixCoder_Code, observable). */
 #define LZB_POS_BLOCK_DONE 0x4C5A4231u
-
-static const Byte k_sig[6] = { 0xFD, '7', 'z', 'X', 'Z', 0 };
 
 extern "C" SRes XzUnpacker_Create(CXzUnpacker *p, ISzAlloc *alloc)
 {
@@ -448,6 +511,216 @@ static void block_payload_done(CXzUnpacker *p)
   p->pos = 0;
   p->alignPos = 0;
 }
+
+/* ---- container framing (xz format 2.1 stream, 3.1 block header, 3.3 padding, 3.4 check, 4 index, 2.1.2 footer,
+ * 2.2 stream padding).  The machine's position inside the container is (state, pos, ...) of the public struct;
+ * pending_of() turns it into "which ELEMENT of the format is being read and how many of its bytes are still
+ * outstanding".  frame_feed() absorbs bytes of that element, frame_close() acts on a complete one.
+ *
+ * observable: the reference asks for input before every step, also before acting on an element that is already
+ * complete (XzDec.c:665-670) -- a header is parsed only when the byte AFTER it has arrived; unpack() keeps that by
+ * returning NEEDS_MORE_INPUT before it comes here.  The stream footer is the one element acted on as soon as its
+ * last byte is in.  Bytes the format fixes (magic, index head, padding) are checked as they arrive: a wrong magic byte
+ * is refused before it is consumed, a wrong index-head or padding byte after. */
+namespace {
+
+const unsigned kMagicBytes = 6, kStreamHeaderBytes = 12, kStreamFooterBytes = 12;      /* xz format 2.1.1, 2.1.2 */
+
+enum Element
+{
+  EL_STREAM_HEADER,      /* magic (6) + stream flags (2) + CRC32 (4)                                         */
+  EL_BLOCK_SIZE,         /* first byte of a block header (size / 4 - 1), or 0x00 = the index follows          */
+  EL_BLOCK_HEADER,       /* the rest of the block header                                                     */
+  EL_BLOCK_PAD,          /* zero bytes up to a multiple of four after the block's payload                    */
+  EL_BLOCK_CHECK,        /* the block's check value                                                          */
+  EL_INDEX_HEAD,         /* index indicator + number of records: known in advance, compared                  */
+  EL_INDEX_RECORDS,      /* (unpadded size, uncompressed size) pairs: hashed, the digest is compared         */
+  EL_INDEX_PAD,          /* zero bytes up to a multiple of four                                              */
+  EL_INDEX_CRC,          /* CRC32 of the index                                                               */
+  EL_STREAM_FOOTER,      /* CRC32 (4) + backward size (4) + stream flags (2) + "YZ"                          */
+  EL_STREAM_PAD          /* zero bytes (a multiple of four) before another stream or the end                 */
+};
+
+struct Pending { Element el; UInt64 bytes; };            /* bytes == 0: the element is complete */
+
+Pending pending_of(const CXzUnpacker *p)
+{
+  switch (p->state)
+  {
+    case XZ_STATE_STREAM_HEADER: return { EL_STREAM_HEADER, (UInt64)kStreamHeaderBytes - p->pos };
+    case XZ_STATE_BLOCK_HEADER:
+      if (p->pos == 0) return { EL_BLOCK_SIZE, 1 };
+      return { EL_BLOCK_HEADER, (UInt64)p->blockHeaderSize - p->pos };
+    case XZ_STATE_BLOCK_FOOTER:
+    {
+      const unsigned pad = (unsigned)(0u - (unsigned)(p->packSize + p->alignPos)) & 3u;
+      if (pad != 0) return { EL_BLOCK_PAD, pad };
+      return { EL_BLOCK_CHECK, (UInt64)XzFlags_GetCheckSize(p->streamFlags) - p->pos };
+    }
+    case XZ_STATE_STREAM_INDEX:
+      if (p->pos < p->indexPreSize) return { EL_INDEX_HEAD, (UInt64)p->indexPreSize - p->pos };
+      if (p->indexPos < p->indexSize) return { EL_INDEX_RECORDS, p->indexSize - p->indexPos };
+      return { EL_INDEX_PAD, (0u - (unsigned)p->indexPos) & 3u };
+    case XZ_STATE_STREAM_INDEX_CRC: return { EL_INDEX_CRC, 4u - (UInt64)p->pos };
+    case XZ_STATE_STREAM_FOOTER: return { EL_STREAM_FOOTER, (UInt64)kStreamFooterBytes - p->pos };
+    default: return { EL_STREAM_PAD, 1 };
+  }
+}
+
+void keep(CXzUnpacker *p, const Byte *src, size_t n)
+{
+  memcpy(p->buf + p->pos, src, n);
+  p->pos += (UInt32)n;
+}
+
+/* the index of a stream starts with bytes the decoder can predict: 0x00 and the number of blocks it has seen */
+void index_begins(CXzUnpacker *p)
+{
+  p->indexPreSize = 1 + Xz_WriteVarInt(p->buf + 1, p->numBlocks);
+  p->indexPos = p->indexPreSize;
+  p->indexSize += p->indexPreSize;
+  Sha256_Final(&p->sha, p->shaDigest);                   /* digest of the records the blocks implied */
+  Sha256_Init(&p->sha);                                  /* ... against the records that are stored    */
+  p->crc = lzb_small_crc32_update(0xFFFFFFFFu, p->buf, p->indexPreSize);
+  p->state = XZ_STATE_STREAM_INDEX;
+}
+
+/* absorb up to n (<= want.bytes, <= what the caller has) bytes of the element being read */
+SRes frame_feed(CXzUnpacker *p, Pending want, const Byte *src, size_t n, size_t *used)
+{
+  static const Byte magic[kMagicBytes] = { 0xFD, '7', 'z', 'X', 'Z', 0 };
+  switch (want.el)
+  {
+    case EL_STREAM_HEADER:
+    {
+      size_t ok = 0;
+      while (ok < n && (p->pos + ok >= kMagicBytes || src[ok] == magic[p->pos + ok])) ok++;
+      keep(p, src, ok);
+      *used = ok;
+      return ok == n ? SZ_OK : SZ_ERROR_NO_ARCHIVE;
+    }
+    case EL_BLOCK_SIZE:
+      keep(p, src, 1);
+      *used = 1;
+      if (src[0] == 0) index_begins(p);
+      p->blockHeaderSize = ((UInt32)p->buf[0] << 2) + 4;
+      return SZ_OK;
+    case EL_BLOCK_HEADER:
+    case EL_BLOCK_CHECK:
+    case EL_INDEX_CRC:
+      keep(p, src, n);
+      *used = n;
+      return SZ_OK;
+    case EL_BLOCK_PAD:
+      for (size_t i = 0; i < n; i++)
+      {
+        p->alignPos++;
+        *used = i + 1;
+        if (src[i] != 0) return SZ_ERROR_CRC;
+      }
+      return SZ_OK;
+    case EL_INDEX_HEAD:
+      for (size_t i = 0; i < n; i++)
+      {
+        *used = i + 1;
+        if (src[i] != p->buf[p->pos++]) return SZ_ERROR_CRC;
+      }
+      return SZ_OK;
+    case EL_INDEX_RECORDS:
+      p->crc = lzb_small_crc32_update(p->crc, src, n);
+      sha_absorb(&p->sha, src, n, false);
+      p->indexPos += n;
+      *used = n;
+      return SZ_OK;
+    case EL_INDEX_PAD:
+      for (size_t i = 0; i < n; i++)
+      {
+        p->crc = lzb_small_crc32_update(p->crc, src + i, 1);
+        p->indexPos++;
+        p->indexSize++;
+        *used = i + 1;
+        if (src[i] != 0) return SZ_ERROR_CRC;
+      }
+      return SZ_OK;
+    case EL_STREAM_FOOTER:
+    {
+      keep(p, src, n);
+      *used = n;
+      if (p->pos != kStreamFooterBytes) return SZ_OK;
+      p->state = XZ_STATE_STREAM_PADDING;
+      p->numStreams++;
+      p->padSize = 0;
+      const Byte *f = p->buf;
+      const bool good = lzb_le32(f) == lzb_small_crc32(f + 4, 6) &&
+                        p->indexSize == (((UInt64)lzb_le32(f + 4) + 1) << 2) &&
+                        p->streamFlags == (((unsigned)f[8] << 8) | f[9]) && f[10] == 'Y' && f[11] == 'Z';
+      return good ? SZ_OK : SZ_ERROR_CRC;
+    }
+    case EL_STREAM_PAD:
+      if (src[0] == 0) { p->padSize++; *used = 1; return SZ_OK; }
+      /* something else begins here: only on a four-byte boundary, and it is not consumed by this element */
+      if (((UInt32)p->padSize & 3) != 0) return SZ_ERROR_NO_ARCHIVE;
+      p->pos = 0;
+      p->state = XZ_STATE_STREAM_HEADER;
+      return SZ_OK;
+  }
+  return SZ_ERROR_FAIL;
+}
+
+/* act on a complete element */
+SRes frame_close(CXzUnpacker *p, Element el)
+{
+  switch (el)
+  {
+    case EL_STREAM_HEADER:
+    {
+      const SRes r = Xz_ParseHeader(&p->streamFlags, p->buf);
+      if (r != SZ_OK) return r;
+      Sha256_Init(&p->sha);
+      p->indexSize = 0;
+      p->numBlocks = 0;
+      p->pos = 0;
+      p->state = XZ_STATE_BLOCK_HEADER;
+      return SZ_OK;
+    }
+    case EL_BLOCK_HEADER:
+    {
+      SRes r = XzBlock_Parse(&p->block, p->buf);
+      if (r != SZ_OK) return r;
+      p->state = XZ_STATE_BLOCK;
+      p->pos = 0;                                        /* (this library's own marker lives here while in BLOCK) */
+      p->packSize = 0;
+      p->unpackSize = 0;
+      XzCheck_Init(&p->check, p->streamFlags & 0xF);
+      return XzDec_Init(&p->decoder, &p->block);
+    }
+    case EL_BLOCK_CHECK:
+    {
+      Byte digest[LZB_XZ_CHECK_SIZE_MAX];
+      const UInt32 n = XzFlags_GetCheckSize(p->streamFlags);
+      p->state = XZ_STATE_BLOCK_HEADER;
+      p->pos = 0;
+      return (XzCheck_Final(&p->check, digest) && memcmp(digest, p->buf, n) != 0) ? SZ_ERROR_CRC : SZ_OK;
+    }
+    case EL_INDEX_PAD:
+    {
+      Byte digest[SHA256_DIGEST_SIZE];
+      p->state = XZ_STATE_STREAM_INDEX_CRC;
+      p->indexSize += 4;
+      p->pos = 0;
+      Sha256_Final(&p->sha, digest);
+      return memcmp(digest, p->shaDigest, SHA256_DIGEST_SIZE) != 0 ? SZ_ERROR_CRC : SZ_OK;
+    }
+    case EL_INDEX_CRC:
+      p->state = XZ_STATE_STREAM_FOOTER;
+      p->pos = 0;
+      return (p->crc ^ 0xFFFFFFFFu) != lzb_le32(p->buf) ? SZ_ERROR_CRC : SZ_OK;
+    default:
+      return SZ_ERROR_FAIL;                              /* the other elements are never "complete and pending" */
+  }
+}
+
+}  // namespace
 
 static SRes unpack(CXzUnpacker *p, LzbContext *ctx, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
                    int finishMode, ECoderStatus *status)
@@ -534,175 +807,13 @@ static SRes unpack(CXzUnpacker *p, LzbContext *ctx, Byte *dest, SizeT *destLen, 
 
     if (rem == 0) { *status = CODER_STATUS_NEEDS_MORE_INPUT; return SZ_OK; }
 
-    switch (p->state)
-    {
-      case XZ_STATE_STREAM_HEADER:
-        if (p->pos < 12)
-        {
-          if (p->pos < 6 && *src != k_sig[p->pos]) return SZ_ERROR_NO_ARCHIVE;
-          p->buf[p->pos++] = *src++;
-          (*srcLen)++;
-        }
-        else
-        {
-          /* parsed when the byte after the header arrives (XzDec.c:677-686) */
-          const SRes r = Xz_ParseHeader(&p->streamFlags, p->buf);
-          if (r != SZ_OK) return r;
-          p->state = XZ_STATE_BLOCK_HEADER;
-          Sha256_Init(&p->sha);
-          p->indexSize = 0;
-          p->numBlocks = 0;
-          p->pos = 0;
-        }
-        break;
-
-      case XZ_STATE_BLOCK_HEADER:
-        if (p->pos == 0)
-        {
-          p->buf[p->pos++] = *src++;
-          (*srcLen)++;
-          if (p->buf[0] == 0)
-          {
-            /* index indicator: what the index must start with is known already (XzDec.c:694-703) */
-            p->indexPreSize = 1 + Xz_WriteVarInt(p->buf + 1, p->numBlocks);
-            p->indexPos = p->indexPreSize;
-            p->indexSize += p->indexPreSize;
-            Sha256_Final(&p->sha, p->shaDigest);
-            Sha256_Init(&p->sha);
-            p->crc = lzb_small_crc32_update(0xFFFFFFFFu, p->buf, p->indexPreSize);
-            p->state = XZ_STATE_STREAM_INDEX;
-          }
-          p->blockHeaderSize = ((UInt32)p->buf[0] << 2) + 4;
-        }
-        else if (p->pos != p->blockHeaderSize)
-        {
-          const UInt32 n = (UInt32)std::min<size_t>(p->blockHeaderSize - p->pos, rem);
-          memcpy(p->buf + p->pos, src, n);
-          p->pos += n; *srcLen += n; src += n;
-        }
-        else
-        {
-          SRes r = XzBlock_Parse(&p->block, p->buf);
-          if (r != SZ_OK) return r;
-          p->state = XZ_STATE_BLOCK;
-          p->pos = 0;                                   /* (unused by the reference in this state) */
-          p->packSize = 0;
-          p->unpackSize = 0;
-          XzCheck_Init(&p->check, p->streamFlags & 0xF);
-          r = XzDec_Init(&p->decoder, &p->block);
-          if (r != SZ_OK) return r;
-        }
-        break;
-
-      case XZ_STATE_BLOCK_FOOTER:
-        if (((p->packSize + p->alignPos) & 3) != 0)
-        {
-          (*srcLen)++;
-          p->alignPos++;
-          if (*src++ != 0) return SZ_ERROR_CRC;
-        }
-        else
-        {
-          const UInt32 check_size = XzFlags_GetCheckSize(p->streamFlags);
-          if (p->pos != check_size)
-          {
-            const UInt32 n = (UInt32)std::min<size_t>(check_size - p->pos, rem);
-            memcpy(p->buf + p->pos, src, n);
-            p->pos += n; *srcLen += n; src += n;
-          }
-          else
-          {
-            Byte digest[LZB_XZ_CHECK_SIZE_MAX];
-            p->state = XZ_STATE_BLOCK_HEADER;
-            p->pos = 0;
-            if (XzCheck_Final(&p->check, digest) && memcmp(digest, p->buf, check_size) != 0) return SZ_ERROR_CRC;
-          }
-        }
-        break;
-
-      case XZ_STATE_STREAM_INDEX:
-        if (p->pos < p->indexPreSize)
-        {
-          (*srcLen)++;
-          if (*src++ != p->buf[p->pos++]) return SZ_ERROR_CRC;
-        }
-        else if (p->indexPos < p->indexSize)
-        {
-          /* the records: hashed, compared (by digest) with the blocks that were seen */
-          const SizeT n = (SizeT)std::min<UInt64>(p->indexSize - p->indexPos, rem);
-          p->crc = lzb_small_crc32_update(p->crc, src, n);
-          sha_absorb(&p->sha, src, n, false);
-          *srcLen += n; src += n; p->indexPos += n;
-        }
-        else if ((p->indexPos & 3) != 0)
-        {
-          const Byte b = *src++;
-          p->crc = lzb_small_crc32_update(p->crc, &b, 1);
-          (*srcLen)++;
-          p->indexPos++;
-          p->indexSize++;
-          if (b != 0) return SZ_ERROR_CRC;
-        }
-        else
-        {
-          Byte digest[SHA256_DIGEST_SIZE];
-          p->state = XZ_STATE_STREAM_INDEX_CRC;
-          p->indexSize += 4;
-          p->pos = 0;
-          Sha256_Final(&p->sha, digest);
-          if (memcmp(digest, p->shaDigest, SHA256_DIGEST_SIZE) != 0) return SZ_ERROR_CRC;
-        }
-        break;
-
-      case XZ_STATE_STREAM_INDEX_CRC:
-        if (p->pos < 4)
-        {
-          (*srcLen)++;
-          p->buf[p->pos++] = *src++;
-        }
-        else
-        {
-          p->state = XZ_STATE_STREAM_FOOTER;
-          p->pos = 0;
-          if ((p->crc ^ 0xFFFFFFFFu) != lzb_le32(p->buf)) return SZ_ERROR_CRC;
-        }
-        break;
-
-      case XZ_STATE_STREAM_FOOTER:
-      {
-        const UInt32 n = (UInt32)std::min<size_t>(12 - p->pos, rem);
-        memcpy(p->buf + p->pos, src, n);
-        p->pos += n; *srcLen += n; src += n;
-        if (p->pos == 12)
-        {
-          p->state = XZ_STATE_STREAM_PADDING;
-          p->numStreams++;
-          p->padSize = 0;
-          const Byte *f = p->buf;
-          const bool ok = p->indexSize == (((UInt64)lzb_le32(f + 4) + 1) << 2) && lzb_le32(f) == lzb_small_crc32(f + 4, 6) &&
-                          p->streamFlags == (((unsigned)f[8] << 8) | f[9]) && f[10] == 'Y' && f[11] == 'Z';
-          if (!ok) return SZ_ERROR_CRC;
-        }
-        break;
-      }
-
-      case XZ_STATE_STREAM_PADDING:
-        if (*src != 0)
-        {
-          if (((UInt32)p->padSize & 3) != 0) return SZ_ERROR_NO_ARCHIVE;
-          p->pos = 0;
-          p->state = XZ_STATE_STREAM_HEADER;
-        }
-        else
-        {
-          (*srcLen)++;
-          src++;
-          p->padSize++;
-        }
-        break;
-
-      case XZ_STATE_BLOCK: break;
-    }
+    /* container framing: one element of the format at a time (below) */
+    const Pending want = pending_of(p);
+    size_t used = 0;
+    const SRes r = want.bytes != 0 ? frame_feed(p, want, src, (size_t)std::min<UInt64>(want.bytes, rem), &used)
+                                   : frame_close(p, want.el);
+    src += used; *srcLen += used;
+    if (r != SZ_OK) return r;
   }
 }
 

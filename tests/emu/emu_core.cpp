@@ -29,8 +29,8 @@ extern "C" int emu_post_units(uint8_t *data, const LzbUnit *units, LzbResult *re
 }
 
 /* the kernel's loop, for one group: fetch -> advance -> (step)* -> ... -> finish */
-extern "C" int emu_decode_units(const uint8_t *packed, uint8_t *out, const LzbUnit *units, LzbResult *results,
-                                uint32_t n)
+template <bool kAhead>
+static int decode_units(const uint8_t *packed, uint8_t *out, const LzbUnit *units, LzbResult *results, uint32_t n)
 {
   std::vector<uint16_t> probs, matched;
   for (uint32_t i = 0; i < n; i++)
@@ -44,7 +44,7 @@ extern "C" int emu_decode_units(const uint8_t *packed, uint8_t *out, const LzbUn
     if (ng * 2 < lzb::kPostScratchBytes) ng = lzb::kPostScratchBytes / 2;
     probs.assign(ns, 0xDEAD);       /* poison: every model entry must be initialised by the decoder */
     matched.assign(ng, 0xDEAD);
-    lzb::UnitDecoderT<1> d;
+    lzb::UnitDecoderT<1, false, kAhead> d;
     const bool stateful = (u.flags & LZB_UNIT_STATEFUL) != 0;
     d.begin(packed + u.src_off, u.src_len, out + u.dst_off, stateful ? u.filter_param : u.dst_cap, u.dict_size,
             probs.data(), matched.data());
@@ -60,4 +60,17 @@ extern "C" int emu_decode_units(const uint8_t *packed, uint8_t *out, const LzbUn
     results[i] = r;
   }
   return 0;
+}
+
+/* ahead = 1: the look-ahead form of the decoder (what one-unit-per-warp launches with few units per SM run) */
+extern "C" int emu_decode_units2(const uint8_t *packed, uint8_t *out, const LzbUnit *units, LzbResult *results,
+                                 uint32_t n, int ahead)
+{
+  return ahead ? decode_units<true>(packed, out, units, results, n) : decode_units<false>(packed, out, units, results, n);
+}
+
+extern "C" int emu_decode_units(const uint8_t *packed, uint8_t *out, const LzbUnit *units, LzbResult *results,
+                                uint32_t n)
+{
+  return decode_units<false>(packed, out, units, results, n);
 }

@@ -19,6 +19,7 @@ SO = os.path.join(HERE, "emu", "_build", "libemu.so")
 SRC = os.path.join(HERE, "emu", "emu_core.cpp")
 
 _lib = None
+AHEAD = 0          # 1: run the look-ahead form of the decoder (UnitDecoderT<1, false, true>); tests switch it
 
 
 def _stale() -> bool:
@@ -39,6 +40,8 @@ def lib():
         _lib = C.CDLL(SO)
         _lib.emu_decode_units.restype = C.c_int
         _lib.emu_decode_units.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        _lib.emu_decode_units2.restype = C.c_int
+        _lib.emu_decode_units2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
         _lib.emu_post_units.restype = C.c_int
         _lib.emu_post_units.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     return _lib
@@ -48,7 +51,7 @@ def decode_units(packed: np.ndarray, out: np.ndarray, units: np.ndarray) -> np.n
     import lzb200
     res = np.zeros(len(units), dtype=lzb200.records.RESULT_DTYPE)
     packed = np.ascontiguousarray(packed, dtype=np.uint8)
-    lib().emu_decode_units(packed.ctypes.data, out.ctypes.data, units.ctypes.data, res.ctypes.data, len(units))
+    lib().emu_decode_units2(packed.ctypes.data, out.ctypes.data, units.ctypes.data, res.ctypes.data, len(units), int(AHEAD))
     return res
 
 

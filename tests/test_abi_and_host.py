@@ -166,7 +166,7 @@ def test_xz_backward_index_matches_oracle(ora):
 class LzbGeometry(C.Structure):       # csrc/lzb_kernels.h
     _fields_ = [("group", C.c_uint32), ("warps_per_cta", C.c_uint32), ("units_per_cta", C.c_uint32), ("ctas", C.c_uint32),
                 ("region_bytes", C.c_uint32), ("smem_stride", C.c_uint32), ("slab_stride", C.c_uint32),
-                ("shared_model", C.c_int), ("slab_bytes", C.c_size_t)]
+                ("shared_model", C.c_int), ("ahead", C.c_int), ("slab_bytes", C.c_size_t)]
 
 
 def test_few_units_launch_plan():
@@ -179,7 +179,7 @@ def test_few_units_launch_plan():
     optin = 232448                                  # B200: 227 KiB per CTA
 
     def default(region=6448, slab=8192, units=36):  # lc3/lp0/pb2: the throughput geometry of lzb_launch_geometry
-        return LzbGeometry(16, units // 2, units, 148, region, region, slab, 1, slab * units * 148)
+        return LzbGeometry(16, units // 2, units, 148, region, region, slab, 1, 0, slab * units * 148)
 
     def run(n, regroup=1, dense=0, **kw):
         g = default(**kw)
@@ -193,18 +193,18 @@ def test_few_units_launch_plan():
         return g
 
     g = run(65536)                                  # the bench batch: throughput mode untouched
-    assert (g.group, g.warps_per_cta, g.units_per_cta, g.smem_stride) == (16, 18, 36, 6448)
+    assert (g.group, g.warps_per_cta, g.units_per_cta, g.smem_stride, g.ahead) == (16, 18, 36, 6448, 0)
     g = run(148 * 16 + 1)                           # one unit too many for a single wave of warps
     assert g.group == 16
-    g = run(2220)                                   # xz4m: 15 per SM, trees fit (15 x 14,640 B)
-    assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 15, 6448 + 8192)
+    g = run(2220)                                   # xz4m: 15 per SM, trees fit (15 x 14,640 B); too many warps to look ahead
+    assert (g.group, g.warps_per_cta, g.smem_stride, g.ahead) == (32, 15, 6448 + 8192, 0)
     g = run(148 * 16)                               # 16 per SM: one warp each, trees stay in the slab
     assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 16, 6448)
-    g = run(1024)                                   # spread: 7 warps on every SM instead of 16 on 64
-    assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 7, 14640)
+    g = run(1024)                                   # spread: 7 warps on every SM instead of 16 on 64; look-ahead decoder
+    assert (g.group, g.warps_per_cta, g.smem_stride, g.ahead) == (32, 7, 14640, 1)
     for n in (1, 148):
         g = run(n)
-        assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 1, 14640)
+        assert (g.group, g.warps_per_cta, g.smem_stride, g.ahead) == (32, 1, 14640, 1)
     g = run(1024, dense=1)                          # LZB_SMEM_MATCHED=0: the old packing
     assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 16, 6448)
     g = run(1024, regroup=0)                        # LZB_GROUP forced: lanes per unit are the caller's

@@ -12,10 +12,13 @@ import cases
 import emubind
 
 
-@pytest.fixture(scope="module")
-def emu():
+@pytest.fixture(scope="module", params=["lean", "ahead"])
+def emu(request):
+    """Both forms of the decoder the kernels instantiate: lean (many units per SM) and look-ahead (a warp per unit)."""
     emubind.lib()
-    return emubind.Emu()
+    emubind.AHEAD = 1 if request.param == "ahead" else 0
+    yield emubind.Emu()
+    emubind.AHEAD = 0
 
 
 @pytest.mark.parametrize("kind", ["lzma", "lzma2"])
@@ -100,6 +103,34 @@ def test_kernel_logic_fused_filter_and_check(emu, ora):
     units["expect"][1] ^= 1
     res = emubind.decode_units(np.concatenate((xz, np.zeros(16, np.uint8))), out, units)
     assert res["res"].tolist() == [0, R.SZ_ERROR_CRC] + [0] * (len(units) - 2)
+
+
+@pytest.mark.needref
+def test_fused_x86_filter_starts_a_block_without_history(emu, ref):
+    """A BCJ filter fused behind a decode starts every block with history 0 -- also when the unit's `expect` field
+    (the stored digest there, the incoming history only for stand-alone x86_Convert calls) has bits 32..34 set.
+    Blocks that begin with E8 candidates at offsets 0..2 are the ones that can tell."""
+    import lzb200
+    R = lzb200.records
+    rng = np.random.default_rng(3)
+    done = 0
+    for trial in range(64):
+        plain = rng.integers(0, 256, 3000, dtype=np.uint8)
+        for at in (0, 1, 2, 7, 9):
+            plain[at] = 0xE8
+            plain[at + 4] = 0x00 if (at + trial) & 1 else 0xFF
+        digest = ref.crc64(plain)
+        if ((digest >> 32) & 7) == 0:
+            continue
+        pk, prop = ref.lzma2_encode(ref.x86_filter_whole(plain, 0, 1), level=1, dict_size=1 << 16)
+        u = R.make_units(1)
+        u["src_len"], u["dst_cap"], u["dict_size"] = len(pk), len(plain), (2 | (prop & 1)) << (prop // 2 + 11)
+        u["codec"], u["finish"], u["filter"], u["check"], u["flags"], u["expect"] = R.CODEC_LZMA2, R.LZMA_FINISH_END, 4, 4, R.UNIT_VERIFY, digest
+        out = np.zeros(len(plain) + 64, np.uint8)
+        res = emubind.decode_units(np.concatenate((pk, np.zeros(16, np.uint8))), out, u)
+        assert int(res["res"][0]) == 0 and np.array_equal(out[: len(plain)], plain), trial
+        done += 1
+    assert done >= 20
 
 
 @pytest.mark.needref

@@ -77,8 +77,14 @@ def test_oracle_streaming_pinned_to_reference(ref, ora):
     run_matrix(ora, ref)
 
 
-def test_kernel_resume_logic_under_emulation(ora):
-    run_matrix(EmuStream(), ora)
+@pytest.mark.parametrize("form", ["lean", "ahead"])
+def test_kernel_resume_logic_under_emulation(ora, form):
+    import emubind
+    emubind.AHEAD = 1 if form == "ahead" else 0
+    try:
+        run_matrix(EmuStream(), ora)
+    finally:
+        emubind.AHEAD = 0
 
 
 @pytest.mark.gpu
@@ -151,13 +157,19 @@ def ring_wrap_streams(ref, count=40):
 
 
 @pytest.mark.needref
-def test_match_of_len_eq_distance_at_the_ring_wrap_under_emulation(ref):
-    for plain, packed, props in ring_wrap_streams(ref):
-        for ic, oc in ((1 << 20, 1 << 20), (4096, 4096), (997, 333)):
-            a = ref.lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
-            b = EmuStream().lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
-            same(a, b)
-            assert np.array_equal(b["out"][: len(plain)], plain)
+@pytest.mark.parametrize("form", ["lean", "ahead"])
+def test_match_of_len_eq_distance_at_the_ring_wrap_under_emulation(ref, form):
+    import emubind
+    emubind.AHEAD = 1 if form == "ahead" else 0
+    try:
+        for plain, packed, props in ring_wrap_streams(ref):
+            for ic, oc in ((1 << 20, 1 << 20), (4096, 4096), (997, 333)):
+                a = ref.lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
+                b = EmuStream().lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
+                same(a, b)
+                assert np.array_equal(b["out"][: len(plain)], plain)
+    finally:
+        emubind.AHEAD = 0
 
 
 @pytest.mark.gpu

@@ -325,8 +325,19 @@ void Lzb_HostFree(void *p);
 SRes Lzb_DecodeUnitsHost(LzbContext *ctx, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
                          const LzbUnit *units, LzbResult *results, size_t n);
 
+/* The same job on SEVERAL GPUs of one box (units are independent, the multi-GPU path is a partition,
+ * not a collective).  ctxs[0..nCtx) are contexts of distinct devices.  The unit table is cut into nCtx contiguous
+ * ranges balanced by unpacked bytes (Lzb_ShardBounds); one host thread per context uploads only the packed bytes of
+ * its range and brings back its own slab of the output.  results[] is filled in unit order; the return value is
+ * the worst per-context status. */
+SRes Lzb_DecodeUnitsHostMulti(LzbContext *const *ctxs, size_t nCtx, const Byte *packed, size_t packedBytes, Byte *out,
+                              size_t outBytes, const LzbUnit *units, LzbResult *results, size_t n);
+
+/* bounds[0..world]: rank r owns units [bounds[r], bounds[r+1]).  Contiguous, balanced by cumulative dst_cap. */
+void Lzb_ShardBounds(const LzbUnit *units, size_t n, size_t world, size_t *bounds);
+
 /* Same with both arenas already resident in DEVICE memory; asynchronous on `stream` (a cudaStream_t;
- * NULL = the CUDA default stream).  d_units / d_results are device arrays.  The packed arena must be
+ * NULL = the CUDA default stream).  Launches of one context are ordered one behind the other, also across streams.  d_units / d_results are device arrays.  The packed arena must be
  * readable up to the next 4-byte boundary past its last unit. */
 SRes Lzb_DecodeUnitsDevice(LzbContext *ctx, const Byte *d_packed, Byte *d_out, const LzbUnit *d_units,
                            LzbResult *d_results, size_t n, unsigned maxLcLp, unsigned maxPb, void *stream);

@@ -117,8 +117,11 @@ template <uint32_t G> LZB_FN void group_copy_fwd(uint8_t *dic, uint32_t dst, uin
     const uint32_t period = dst - src;
     if (period == 1)
     {
-      const uint8_t b = dic[src];
-      for (uint32_t i = lane; i < n; i += G) dic[dst + i] = b;
+      /* a byte run (rep0 = 1).  One byte per lane and trip is enough: a 16-byte-per-lane fill was measured on data
+       * that is nothing but runs and changed nothing (165 vs 169 GB/s out: the run's ~14 modelled bits, not its
+       * stores, are what a full-length run costs; profiles/r02_copy_width.md) */
+      const uint32_t b = dic[src];
+      for (uint32_t i = lane; i < n; i += G) dic[dst + i] = (uint8_t)b;
     }
     else
     {
@@ -594,8 +597,6 @@ template <uint32_t G, bool kSmem = false, bool kAhead = false> struct UnitDecode
     stp(a, np);
     return c;
   }
-  LZB_FN uint32_t rc_bit_at(uint32_t a) { return bit_sel(a, 0u, 1u); }
-
   /* the same through a generic pointer (matched-literal trees: HBM slab or shared memory) */
   LZB_FN uint32_t rc_bit(uint16_t *p)
   {
@@ -606,6 +607,8 @@ template <uint32_t G, bool kSmem = false, bool kAhead = false> struct UnitDecode
     *p = (uint16_t)np;
     return c;
   }
+
+  LZB_FN uint32_t rc_bit_at(uint32_t a) { return bit_sel(a, 0u, 1u); }
 
   /* Walks down a binary tree stored as t[1 .. 2^n), kept in terms of the node's model ADDRESS A (node m of the
    * tree whose element 0 is at L: A = L + 2m): the child address is 2A + (bit ? 2 - L : -L) -- the bit step
@@ -766,12 +769,16 @@ template <uint32_t G, bool kSmem = false, bool kAhead = false> struct UnitDecode
     total_pos += cur;
   }
 
+#include "lzb_core_lean.inc"
+
   /* One LZMA symbol: the body of LzmaDec_DecodeReal's loop, LzmaDec.c:153-410.
    * Returns 0, 1 for SZ_ERROR_DATA (nothing is committed then), 2 for the end marker.
    * left_over receives the part of a match the output limit cut off (remainLen).
+   * Below: the look-ahead form (the lean form is decode_symbol_lean, lzb_core_lean.inc).
    * top_up() calls: at most six modelled bits (or 33 direct bits) between two of them. */
   LZB_FN int decode_symbol(uint32_t limit, uint32_t &left_over)
   {
+    if (!kAhead) return decode_symbol_lean(limit, left_over);
     const uint32_t ps = total_pos & pb_mask;
     left_over = 0;
     top_up();

@@ -14,6 +14,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <string>
 #include <thread>
 
 /* ------------------------------------------------------------------ errors ----------------- */
@@ -550,6 +552,63 @@ extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t pa
   return ret;
 }
 
+/* ------------------------------------------------------------------ several GPUs of one box --- */
+extern "C" void Lzb_ShardBounds(const LzbUnit *units, size_t n, size_t world, size_t *bounds)
+{
+  if (world == 0) return;
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; i++) total += units[i].dst_cap;
+  bounds[0] = 0;
+  size_t i = 0;
+  uint64_t acc = 0;
+  for (size_t r = 1; r < world; r++)
+  {
+    /* the first unit whose cumulative size reaches r / world of the total closes range r - 1 */
+    const double target = (double)total * (double)r / (double)world;
+    while (i < n && (double)acc < target) acc += units[i++].dst_cap;
+    bounds[r] = i;
+  }
+  bounds[world] = n;
+}
+
+extern "C" SRes Lzb_DecodeUnitsHostMulti(LzbContext *const *ctxs, size_t nCtx, const Byte *packed, size_t packedBytes, Byte *out,
+                                         size_t outBytes, const LzbUnit *units, LzbResult *results, size_t n)
+{
+  if (nCtx == 0 || !ctxs) { lzb_set_error("no context"); return SZ_ERROR_PARAM; }
+  if (nCtx == 1) return Lzb_DecodeUnitsHost(ctxs[0], packed, packedBytes, out, outBytes, units, results, n);
+  std::vector<size_t> bounds(nCtx + 1);
+  Lzb_ShardBounds(units, n, nCtx, bounds.data());
+  std::vector<SRes> verdict(nCtx, SZ_OK);
+  std::vector<std::string> errors(nCtx);
+  std::vector<std::thread> workers;
+  for (size_t r = 0; r < nCtx; r++)
+  {
+    workers.emplace_back([&, r]()
+    {
+      const size_t lo = bounds[r], hi = bounds[r + 1];
+      if (lo == hi) return;
+      /* this range's windows into the two arenas */
+      uint64_t s_lo = ~0ull, s_hi = 0, d_lo = ~0ull, d_hi = 0;
+      for (size_t i = lo; i < hi; i++)
+      {
+        s_lo = std::min<uint64_t>(s_lo, units[i].src_off); s_hi = std::max<uint64_t>(s_hi, units[i].src_off + units[i].src_len);
+        d_lo = std::min<uint64_t>(d_lo, units[i].dst_off); d_hi = std::max<uint64_t>(d_hi, units[i].dst_off + units[i].dst_cap);
+      }
+      if (s_hi > packedBytes || d_hi > outBytes) { verdict[r] = SZ_ERROR_PARAM; errors[r] = "a unit exceeds its arena"; return; }
+      std::vector<LzbUnit> mine(units + lo, units + hi);
+      for (LzbUnit &u : mine) { u.src_off -= s_lo; u.dst_off -= d_lo; }
+      verdict[r] = Lzb_DecodeUnitsHost(ctxs[r], packed + s_lo, (size_t)(s_hi - s_lo), out + d_lo, (size_t)(d_hi - d_lo),
+                                       mine.data(), results + lo, hi - lo);
+      if (verdict[r] != SZ_OK) errors[r] = Lzb_LastError();          /* (the error text is per thread) */
+    });
+  }
+  for (std::thread &t : workers) t.join();
+  SRes worst = SZ_OK;
+  for (size_t r = 0; r < nCtx; r++)
+    if (verdict[r] != SZ_OK && worst == SZ_OK) { worst = verdict[r]; lzb_set_error("GPU %zu of %zu: %s", r, nCtx, errors[r].c_str()); }
+  return worst;
+}
+
 /* Run a few units whose arenas the caller already placed in device memory; unit table and results are
  * host arrays.  Synchronous.  Used by the stateful SDK objects (lzb_state.cu). */
 SRes lzb_run_resident(LzbContext *c, const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *units, LzbResult *results, size_t n)
@@ -565,6 +624,35 @@ SRes lzb_run_resident(LzbContext *c, const uint8_t *d_packed, uint8_t *d_out, co
   if (!lzb_cuda_ok(cudaMemcpyAsync(results, s.d_results, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results") ||
       !lzb_cuda_ok(cudaStreamSynchronize(s.stream), "decode kernel")) return SZ_ERROR_FAIL;
   return SZ_OK;
+}
+
+/* One call of a resumable decoder object (lzb_state.cu).  Everything the call needs travels in two small uploads
+ * from page-locked memory -- the scalars of the object (-> the header of its device-resident state) and one block
+ * holding [LzbUnit | LzbResult | parked bytes + new input] -- then the launch, then the scalars, the result and the
+ * newly written part of the dictionary mirror come back, all queued on one stream with a single wait at the end.
+ * The size of the new dictionary part is only known afterwards: `guess` bytes are fetched with the rest of the
+ * queue, the caller fetches what lies beyond (rare) once it has the scalars. */
+SRes lzb_run_stateful(LzbContext *c, uint8_t *d_block, const uint8_t *h_block, size_t block_bytes, const LzbUnit *unit,
+                      uint8_t *d_state, LzbStreamState *h_state, LzbResult *h_result,
+                      const uint8_t *d_dic, Byte *dic, size_t dic_from, size_t guess)
+{
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return SZ_ERROR_FAIL;
+  LzbSlot &s = c->slot[0];
+  const ModelBytes model = model_bytes_for(unit, 1);
+  if (!lzb_slot_reserve(c, s, 0, 0, 1, slab_bytes_for(model))) return SZ_ERROR_MEM;
+  const LzbUnit *d_unit = reinterpret_cast<const LzbUnit *>(d_block);
+  LzbResult *d_result = reinterpret_cast<LzbResult *>(d_block + LZB_STATEFUL_RESULT_AT);
+  bool ok = lzb_cuda_ok(cudaMemcpyAsync(d_state, h_state, sizeof(LzbStreamState), cudaMemcpyHostToDevice, s.stream), "H2D decoder scalars") &&
+            lzb_cuda_ok(cudaMemcpyAsync(d_block, h_block, block_bytes, cudaMemcpyHostToDevice, s.stream), "H2D unit + input");
+  if (!ok) return SZ_ERROR_FAIL;
+  const int rc = lzb_launch_decode(d_block + LZB_STATEFUL_INPUT_AT, const_cast<uint8_t *>(d_dic), d_unit, d_result, 1, s.d_ticket,
+                                   model.smem, model.gmem, s.d_slab, s.stream);
+  if (rc != 0) { lzb_set_error("decode launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return SZ_ERROR_FAIL; }
+  ok = lzb_cuda_ok(cudaMemcpyAsync(h_state, d_state, sizeof(LzbStreamState), cudaMemcpyDeviceToHost, s.stream), "D2H decoder scalars") &&
+       lzb_cuda_ok(cudaMemcpyAsync(h_result, d_result, sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H result");
+  if (ok && guess) ok = lzb_cuda_ok(cudaMemcpyAsync(dic + dic_from, d_dic + dic_from, guess, cudaMemcpyDeviceToHost, s.stream), "D2H dictionary");
+  return (ok && lzb_cuda_ok(cudaStreamSynchronize(s.stream), "stateful decode")) ? SZ_OK : SZ_ERROR_FAIL;
 }
 
 /* One archive, several dependent passes over the same device-resident arenas (7z folder path): upload the
@@ -650,6 +738,102 @@ extern "C" SRes LzmaProps_Decode(CLzmaProps *p, const Byte *data, unsigned size)
   return SZ_OK;
 }
 
+/* ------------------------------------------------------------------ callers that do not batch -- */
+/* LzmaUncompress / LzmaDecode decode ONE stream per call; a stream alone occupies one warp of one SM for its whole
+ * decode (a 64 KiB stream: ~15 ms), so a host that calls from many threads -- the GPU analogue of the reference's
+ * one-unit-per-thread use -- would queue up behind the context lock, one launch each.  Instead concurrent small
+ * calls are COMBINED: a caller leaves its request in a list; whoever finds no launch in flight becomes the leader,
+ * takes everything in the list (its own request included), runs it as one batch through Lzb_DecodeUnitsHost and
+ * hands the results out; callers that arrive meanwhile form the next batch.  One caller alone pays two extra host
+ * copies of its bytes; N concurrent callers finish in about the time of one.  Still no CPU fallback. */
+namespace {
+
+const size_t kCombineMaxBytes = (size_t)8 << 20;      /* larger calls go straight to Lzb_DecodeUnitsHost */
+
+struct OneCall
+{
+  const Byte *src = nullptr;
+  Byte *dest = nullptr;
+  LzbUnit unit;
+  LzbResult res;
+  SRes call_res = SZ_OK;
+  bool done = false;
+  std::condition_variable cv;
+};
+
+struct Combiner
+{
+  std::mutex mu;
+  std::vector<OneCall *> waiting;
+  bool busy = false;                                  /* a leader is running a batch */
+  Byte *h_in = nullptr, *h_out = nullptr;             /* page-locked staging arenas, grown on demand */
+  size_t in_cap = 0, out_cap = 0;
+  std::vector<LzbUnit> units;
+  std::vector<LzbResult> results;
+} g_combiner;
+
+bool stage_reserve(Byte *&p, size_t &cap, size_t need)
+{
+  if (need <= cap) return true;
+  Lzb_HostFree(p);
+  p = (Byte *)Lzb_HostAlloc(need + need / 2 + 4096);
+  cap = p ? need + need / 2 + 4096 : 0;
+  return p != nullptr;
+}
+
+void run_batch(LzbContext *c, std::vector<OneCall *> &batch)
+{
+  Combiner &q = g_combiner;                           /* staging is the leader's while `busy` is set */
+  const size_t n = batch.size();
+  q.units.resize(n); q.results.resize(n);
+  size_t in_bytes = 0, out_bytes = 0;
+  for (size_t i = 0; i < n; i++)
+  {
+    LzbUnit &u = q.units[i];
+    u = batch[i]->unit;
+    u.src_off = in_bytes; u.dst_off = out_bytes;
+    in_bytes += ((size_t)u.src_len + 15) & ~(size_t)15;
+    out_bytes += ((size_t)u.dst_cap + 15) & ~(size_t)15;
+  }
+  SRes r = SZ_OK;
+  if (!stage_reserve(q.h_in, q.in_cap, in_bytes + 64) || !stage_reserve(q.h_out, q.out_cap, out_bytes + 64)) r = SZ_ERROR_MEM;
+  if (r == SZ_OK)
+  {
+    for (size_t i = 0; i < n; i++) memcpy(q.h_in + q.units[i].src_off, batch[i]->src, q.units[i].src_len);
+    r = Lzb_DecodeUnitsHost(c, q.h_in, in_bytes + 64, q.h_out, out_bytes + 64, q.units.data(), q.results.data(), n);
+  }
+  for (size_t i = 0; i < n; i++)
+  {
+    OneCall &o = *batch[i];
+    o.call_res = r;
+    if (r != SZ_OK) continue;
+    o.res = q.results[i];
+    const size_t made = std::min<size_t>(o.res.dst_done, q.units[i].dst_cap);
+    if (made) memcpy(o.dest, q.h_out + q.units[i].dst_off, made);
+  }
+}
+
+SRes combined_decode(LzbContext *c, OneCall &me)
+{
+  Combiner &q = g_combiner;
+  std::unique_lock<std::mutex> lk(q.mu);
+  q.waiting.push_back(&me);
+  while (!me.done && q.busy) me.cv.wait(lk);
+  if (me.done) return me.call_res;                    /* a leader served this call */
+  q.busy = true;                                      /* lead: everything that is waiting now, this call included */
+  std::vector<OneCall *> batch;
+  batch.swap(q.waiting);
+  lk.unlock();
+  run_batch(c, batch);
+  lk.lock();
+  q.busy = false;
+  for (OneCall *o : batch) if (o != &me) { o->done = true; o->cv.notify_one(); }
+  if (!q.waiting.empty()) q.waiting.front()->cv.notify_one();      /* the next batch gets its leader */
+  return me.call_res;
+}
+
+}  // namespace
+
 /* ------------------------------------------------------------------ one-call raw LZMA -------- */
 extern "C" SRes LzmaDecode(Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen, const Byte *propData,
                            unsigned propSize, ELzmaFinishMode finishMode, ELzmaStatus *status, ISzAlloc *alloc)
@@ -666,18 +850,22 @@ extern "C" SRes LzmaDecode(Byte *dest, SizeT *destLen, const Byte *src, SizeT *s
   if (inSize > 0xFFFFFFFFull || outSize > 0xFFFFFFFFull) { lzb_set_error("single stream larger than 4 GiB"); return SZ_ERROR_UNSUPPORTED; }
   LzbContext *c = lzb_default_context();
   if (!c) return SZ_ERROR_FAIL;
-  LzbUnit u;
-  memset(&u, 0, sizeof u);
+  OneCall me;
+  memset(&me.unit, 0, sizeof me.unit);
+  LzbUnit &u = me.unit;
   u.src_len = (uint32_t)inSize; u.dst_cap = (uint32_t)outSize; u.dict_size = pr.dicSize;
   u.codec = LZB_CODEC_LZMA; u.lc = (uint8_t)pr.lc; u.lp = (uint8_t)pr.lp; u.pb = (uint8_t)pr.pb;
   u.finish = (uint8_t)finishMode;
-  LzbResult res;
-  r = Lzb_DecodeUnitsHost(c, src, inSize, dest, outSize, &u, &res, 1);
+  me.src = src; me.dest = dest;
+  if (inSize + outSize <= kCombineMaxBytes)
+    r = combined_decode(c, me);                /* small call: shares a launch with whoever else is calling right now */
+  else
+    r = Lzb_DecodeUnitsHost(c, src, inSize, dest, outSize, &u, &me.res, 1);
   if (r != SZ_OK) return r;
-  *srcLen = res.src_used;
-  *destLen = res.dst_done;
-  *status = (ELzmaStatus)res.status;
-  return res.res;
+  *srcLen = me.res.src_used;
+  *destLen = me.res.dst_done;
+  *status = (ELzmaStatus)me.res.status;
+  return me.res.res;
 }
 
 extern "C" int LzmaUncompress(unsigned char *dest, size_t *destLen, const unsigned char *src, SizeT *srcLen,

@@ -65,6 +65,13 @@ SRes lzb_flow_then_checks(LzbContext *c, const Byte *packed, size_t packedBytes,
 
 SRes lzb_run_resident(LzbContext *c, const uint8_t *d_packed, uint8_t *d_out, const LzbUnit *units, LzbResult *results, size_t n);
 
+/* one call of a resumable decoder object: block = [LzbUnit | LzbResult | input bytes] at these offsets */
+#define LZB_STATEFUL_RESULT_AT 64
+#define LZB_STATEFUL_INPUT_AT 128
+SRes lzb_run_stateful(LzbContext *c, uint8_t *d_block, const uint8_t *h_block, size_t block_bytes, const LzbUnit *unit,
+                      uint8_t *d_state, LzbStreamState *h_state, LzbResult *h_result,
+                      const uint8_t *d_dic, Byte *dic, size_t dic_from, size_t guess);
+
 /* little helpers */
 static inline uint32_t lzb_le32(const Byte *p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 static inline uint64_t lzb_le64(const Byte *p) { return (uint64_t)lzb_le32(p) | ((uint64_t)lzb_le32(p + 4) << 32); }

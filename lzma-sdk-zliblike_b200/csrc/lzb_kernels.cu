@@ -160,7 +160,9 @@ lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict_
       {
         LzbResult r;
         d.finish_unit(r);
-        if (!(u.flags & LZB_UNIT_STATEFUL)) post_process<G>(u, r, dst, region, reinterpret_cast<uint8_t *>(matched));
+        /* (inlined on purpose: out of line, with the unit and result records forced into local memory, the dense
+         * instantiation ran 2 % slower -- profiles/r02_kernel_log.md) */
+        if (!(u.flags & LZB_UNIT_STATEFUL)) post_process<G>(u, r, dst, region, reinterpret_cast<uint8_t *>(matched), kSharedModel ? region_bytes : kPostSmemBytes);
         if (Grp::lane() == 0) results[ui] = r;
         Grp::sync();
         if (kFlow && flow.done) flow_done<G>(flow, ui, n_units);
@@ -189,7 +191,7 @@ lzb_post_only_kernel(uint8_t *__restrict__ data, const LzbUnit *__restrict__ uni
   const LzbUnit u = units[i];
   LzbResult r;
   r.res = LZB_SZ_OK; r.status = LZB_ST_NOT_SPECIFIED; r.src_used = 0; r.dst_done = u.dst_cap; r.check = 0;
-  post_process<32, true>(u, r, data + u.dst_off, scratch[warp], scratch[warp]);
+  post_process<32, true>(u, r, data + u.dst_off, scratch[warp], scratch[warp], kPostScratchBytes);
   if (lane == 0) results[i] = r;
 }
 
@@ -318,7 +320,7 @@ static uint32_t env_u32(const char *name, uint32_t dflt)
 }
 
 static int g_dev_sms = 0;
-static uint32_t g_ahead_max_warps = 8;      /* LZB_AHEAD_WARPS overrides (0 = never), read once */
+static uint32_t g_ahead_max_warps = 16;     /* LZB_AHEAD_WARPS overrides (0 = never), read once */
 static size_t g_dev_smem_optin = 0;
 
 static cudaError_t query_device()
@@ -420,10 +422,11 @@ extern "C" void lzb_plan_few_units(LzbGeometry *gp, uint32_t n_units, size_t sme
     const uint32_t full = g.region_bytes + g.slab_stride;
     if (g.warps_per_cta <= (uint32_t)(smem_optin / full)) g.smem_stride = full;
   }
-  /* With at most kAheadMaxWarps units on an SM the issue slots are mostly idle and a unit is bound by its own
-   * dependency chain: the look-ahead form of the decoder (predicated normalisation, both children of a tree node
-   * loaded while the bit is decided; lzb_core.cuh) trades ~25 % more issued instructions for a shorter chain.
-   * Above that the issue slots are the bound again and the lean form wins (profiles/r02_b_*). */
+  /* One unit per warp (at most 16 warps on an SM): a unit is bound by its own dependency chain, so the look-ahead form
+   * of the decoder (predicated normalisation, both children of a tree node loaded while the bit is decided;
+   * lzb_core.cuh) trades ~15 % more issued instructions for a shorter chain: +18 % at 7 warps per SM, +21 % at 1,
+   * still +6..8 % at 15-16 (profiles/r02_d_*, r02_e_*).  With two units per warp the issue slots are the bound and the
+   * lean form wins by 18 % (profiles/r02_b_*). */
   g.ahead = (g.shared_model && g.group == 32 && g.warps_per_cta <= g_ahead_max_warps) ? 1 : 0;
 }
 

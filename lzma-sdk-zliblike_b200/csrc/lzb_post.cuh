@@ -11,8 +11,9 @@
  *           boundary and runs the scalar converter up to the next lane's start.
  *  Delta    (Delta.c:43-62)   out[i] = in[i] + out[i-d] is a prefix sum per residue class mod d:
  *           per-lane column sums -> exclusive scan across lanes -> second sweep.
- *  CRC      (7zCrc.c, 7zCrcOpt.c, XzCrc64.c)  per-lane register over a contiguous segment, then the
- *           G partial registers are aligned with x^(8*bytes_after) mod P and XOR-reduced.
+ *  CRC      (7zCrc.c, 7zCrcOpt.c, XzCrc64.c)  slicing tables in the group's scratch (four bytes per dependent step
+ *           when they fit), per-lane register over a contiguous segment, then the G partial registers are aligned
+ *           with x^(8*bytes_after) mod P and XOR-reduced.
  */
 #pragma once
 
@@ -214,23 +215,61 @@ template <uint32_t G> LZB_FN void lane_segment(uint32_t size, uint32_t &begin, u
   end = size - begin < seg ? size : begin + seg;
 }
 
-/* CRC-32 as CrcCalc (7zCrc.c:44): preset all-ones, final inversion */
-template <uint32_t G> LZB_FN uint32_t crc32_group(const uint8_t *data, uint32_t size, uint32_t *table /* 256 entries */)
+/* Slicing tables in the group's scratch: table k answers "what does this byte contribute once k more bytes have
+ * gone through the register" (T0 = the classic byte table; Tk[i] = T0[Tk-1[i] & 0xFF] ^ (Tk-1[i] >> 8); the
+ * reference's CrcGenerateTable builds the same family, 7zCrc.c:49-74).  With four tables a lane folds an aligned
+ * 32-bit word per step -- one dependent shared-memory round trip per four bytes instead of one per byte. */
+template <uint32_t G, class T> LZB_FN void crc_tables(T *table, T poly, uint32_t slices)
 {
   typedef Group<G> Grp;
   const uint32_t lane = Grp::lane();
   Grp::sync();
-  for (uint32_t i = lane; i < 256; i += G)               /* CrcGenerateTable, 7zCrc.c:49-60 */
+  for (uint32_t i = lane; i < 256; i += G)
   {
-    uint32_t r = i;
-    for (int k = 0; k < 8; k++) r = (r >> 1) ^ (kPoly32 & (0u - (r & 1)));
+    T r = (T)i;
+    for (int k = 0; k < 8; k++) r = (r >> 1) ^ (poly & (T)(0 - (r & 1)));
     table[i] = r;
   }
   Grp::sync();
+  for (uint32_t k = 1; k < slices; k++)
+  {
+    for (uint32_t i = lane; i < 256; i += G)
+    {
+      const T r = table[(k - 1) * 256 + i];
+      table[k * 256 + i] = table[(uint32_t)(r & 0xFF)] ^ (r >> 8);
+    }
+    Grp::sync();
+  }
+}
+
+/* the register of one lane over its segment [begin, end) of data, starting from v */
+template <class T> LZB_FN T crc_segment(const uint8_t *data, uint32_t begin, uint32_t end, T v, const T *table, uint32_t slices)
+{
+  uint32_t i = begin;
+  if (slices >= 4)
+  {
+    while (i < end && (((uintptr_t)(data + i)) & 3u) != 0) { v = table[(uint32_t)((v ^ data[i]) & 0xFF)] ^ (v >> 8); i++; }
+    for (; i + 4 <= end; i += 4)
+    {
+      const uint32_t w = *reinterpret_cast<const uint32_t *>(data + i) ^ (uint32_t)v;
+      v = (sizeof(T) == 8 ? (T)((uint64_t)v >> 32) : (T)0) ^
+          table[768 + (w & 0xFF)] ^ table[512 + ((w >> 8) & 0xFF)] ^ table[256 + ((w >> 16) & 0xFF)] ^ table[w >> 24];
+    }
+  }
+  for (; i < end; i++) v = table[(uint32_t)((v ^ data[i]) & 0xFF)] ^ (v >> 8);
+  return v;
+}
+
+/* CRC-32 as CrcCalc (7zCrc.c:44): preset all-ones, final inversion.  scratch_bytes: what `table` may use. */
+template <uint32_t G> LZB_FN uint32_t crc32_group(const uint8_t *data, uint32_t size, uint32_t *table, uint32_t scratch_bytes)
+{
+  typedef Group<G> Grp;
+  const uint32_t lane = Grp::lane();
+  const uint32_t slices = scratch_bytes >= 4096 ? 4u : 1u;
+  crc_tables<G, uint32_t>(table, kPoly32, slices);
   uint32_t begin, end;
   lane_segment<G>(size, begin, end);
-  uint32_t v = lane == 0 ? 0xFFFFFFFFu : 0u;
-  for (uint32_t i = begin; i < end; i++) v = table[(v ^ data[i]) & 0xFF] ^ (v >> 8);
+  uint32_t v = crc_segment<uint32_t>(data, begin, end, lane == 0 ? 0xFFFFFFFFu : 0u, table, slices);
   v = mulmod32(v, xpow32(size - end));
   for (uint32_t m = G >> 1; m != 0; m >>= 1) v ^= Grp::shfl_xor(v, m);
   Grp::sync();
@@ -238,22 +277,15 @@ template <uint32_t G> LZB_FN uint32_t crc32_group(const uint8_t *data, uint32_t 
 }
 
 /* CRC-64/XZ as Crc64Calc (XzCrc64.c:30) */
-template <uint32_t G> LZB_FN uint64_t crc64_group(const uint8_t *data, uint32_t size, uint64_t *table /* 256 entries */)
+template <uint32_t G> LZB_FN uint64_t crc64_group(const uint8_t *data, uint32_t size, uint64_t *table, uint32_t scratch_bytes)
 {
   typedef Group<G> Grp;
   const uint32_t lane = Grp::lane();
-  Grp::sync();
-  for (uint32_t i = lane; i < 256; i += G)               /* Crc64GenerateTable, XzCrc64.c:9-20 */
-  {
-    uint64_t r = i;
-    for (int k = 0; k < 8; k++) r = (r >> 1) ^ (kPoly64 & (0ull - (r & 1)));
-    table[i] = r;
-  }
-  Grp::sync();
+  const uint32_t slices = scratch_bytes >= 8192 ? 4u : 1u;
+  crc_tables<G, uint64_t>(table, kPoly64, slices);
   uint32_t begin, end;
   lane_segment<G>(size, begin, end);
-  uint64_t v = lane == 0 ? ~0ull : 0ull;
-  for (uint32_t i = begin; i < end; i++) v = table[(v ^ data[i]) & 0xFF] ^ (v >> 8);
+  uint64_t v = crc_segment<uint64_t>(data, begin, end, lane == 0 ? ~0ull : 0ull, table, slices);
   v = mulmod64(v, xpow64(size - end));
   for (uint32_t m = G >> 1; m != 0; m >>= 1) v ^= Grp::shfl_xor(v, m);
   Grp::sync();
@@ -387,7 +419,8 @@ template <uint32_t G> LZB_FN void delta_encode_group(uint8_t *data, uint32_t n, 
 /* kRisc: also the stateless RISC converters (only the stand-alone / second-pass kernel carries them, the
  * fused decode kernel stays lean: BCJ x86 and Delta are what the reference's own writers emit). */
 template <uint32_t G, bool kRisc = false>
-LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t *scratch, uint8_t *big_scratch)
+LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t *scratch, uint8_t *big_scratch,
+                         uint32_t scratch_bytes = kPostSmemBytes)
 {
   if (r.res != LZB_SZ_OK) return;
   const uint32_t n = r.dst_done;
@@ -409,8 +442,8 @@ LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t 
     const uint32_t done = risc_convert_group<G>(data, n, u.filter, u.filter_param, (u.flags & 2) != 0);
     if (u.flags & 4) r.src_used = done;
   }
-  if (u.check == LZB_CHECK_CRC32) r.check = crc32_group<G>(data, n, reinterpret_cast<uint32_t *>(scratch));
-  else if (u.check == LZB_CHECK_CRC64) r.check = crc64_group<G>(data, n, reinterpret_cast<uint64_t *>(scratch));
+  if (u.check == LZB_CHECK_CRC32) r.check = crc32_group<G>(data, n, reinterpret_cast<uint32_t *>(scratch), scratch_bytes);
+  else if (u.check == LZB_CHECK_CRC64) r.check = crc64_group<G>(data, n, reinterpret_cast<uint64_t *>(scratch), scratch_bytes);
   if ((u.flags & LZB_UNIT_VERIFY) && u.check != LZB_CHECK_NONE && r.check != u.expect) r.res = LZB_SZ_ERROR_CRC;
 }
 

@@ -22,13 +22,18 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 struct LzbCtl
 {
   uint64_t magic;
   uint8_t *d_state; size_t state_bytes;
   uint8_t *d_dic;   size_t dic_cap;
-  uint8_t *d_in;    size_t in_cap;
+  uint8_t *d_in;    size_t in_cap;      /* device block of a call: [LzbUnit | LzbResult | parked bytes + input] */
+  uint8_t *h_stage; size_t stage_cap;   /* page-locked: [LzbStreamState | LzbResult | pad | the same block]   */
 };
+static const size_t kStageStateAt = 0, kStageResultAt = 128, kStageBlockAt = 192;
+static const size_t kDicGuessBytes = (size_t)1 << 20;
 #define LZB_CTL_MAGIC 0x4C5A4243544C3032ull
 
 static LzbCtl *ctl_of(CLzmaDec *p) { return (LzbCtl *)(void *)p->probs; }
@@ -37,8 +42,9 @@ static void ctl_release_device(LzbCtl *c)
 {
   if (!c || c->magic != LZB_CTL_MAGIC) return;
   cudaFree(c->d_state); cudaFree(c->d_dic); cudaFree(c->d_in);
-  c->d_state = c->d_dic = c->d_in = nullptr;
-  c->state_bytes = c->dic_cap = c->in_cap = 0;
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  c->d_state = c->d_dic = c->d_in = c->h_stage = nullptr;
+  c->state_bytes = c->dic_cap = c->in_cap = c->stage_cap = 0;
 }
 
 static SRes alloc_ctl(CLzmaDec *p, const CLzmaProps *pr, ISzAlloc *alloc)
@@ -125,6 +131,11 @@ template <class T> static bool grow_dev(T *&ptr, size_t &cap, size_t need, const
   cudaFree(ptr);
   ptr = nullptr; cap = 0;
   if (!lzb_cuda_ok(cudaMalloc((void **)&ptr, need + 64), what)) return false;
+  /* zeroed: a call may fetch dictionary bytes the decoder has not written yet (the speculative part of the download),
+   * and nothing an earlier user of this device memory left behind may reach the caller */
+  /* (cudaMemset runs on the legacy default stream, which the context's non-blocking streams do not wait for: it
+   * must have finished before anything is uploaded into the new buffer) */
+  if (!lzb_cuda_ok(cudaMemset(ptr, 0, need + 64), what) || !lzb_cuda_ok(cudaDeviceSynchronize(), what)) return false;
   cap = need;
   return true;
 }
@@ -148,12 +159,23 @@ static SRes step(CLzmaDec *p, CLzma2Dec *l2, SizeT dicLimit, const Byte *src, Si
   const size_t state_bytes = sizeof(LzbStreamState) + (size_t)lzb_num_probs(mlc, mlp, mpb) * 2;
   const unsigned prefix = p->tempBufSize;
   const size_t total_in = (size_t)prefix + inSize;
+  const size_t block_bytes = LZB_STATEFUL_INPUT_AT + total_in + 16;
   if (!grow_dev(ctl->d_state, ctl->state_bytes, state_bytes, "cudaMalloc decoder state") ||
       !grow_dev(ctl->d_dic, ctl->dic_cap, p->dicBufSize, "cudaMalloc dictionary mirror") ||
-      !grow_dev(ctl->d_in, ctl->in_cap, total_in + 16, "cudaMalloc input staging"))
+      !grow_dev(ctl->d_in, ctl->in_cap, block_bytes, "cudaMalloc input staging"))
     return SZ_ERROR_MEM;
+  if (kStageBlockAt + block_bytes > ctl->stage_cap)
+  {
+    if (ctl->h_stage) cudaFreeHost(ctl->h_stage);
+    ctl->h_stage = nullptr; ctl->stage_cap = 0;
+    const size_t want = kStageBlockAt + block_bytes + block_bytes / 4 + 4096;
+    if (!lzb_cuda_ok(cudaHostAlloc((void **)&ctl->h_stage, want, cudaHostAllocDefault), "cudaHostAlloc decoder staging")) return SZ_ERROR_MEM;
+    ctl->stage_cap = want;
+  }
 
-  LzbStreamState st;
+  LzbStreamState &st = *reinterpret_cast<LzbStreamState *>(ctl->h_stage + kStageStateAt);
+  LzbResult &x = *reinterpret_cast<LzbResult *>(ctl->h_stage + kStageResultAt);
+  uint8_t *block = ctl->h_stage + kStageBlockAt;
   memset(&st, 0, sizeof st);
   st.range = p->range; st.code = p->code; st.state = p->state;
   for (int i = 0; i < 4; i++) st.rep[i] = p->reps[i];
@@ -168,14 +190,8 @@ static SRes step(CLzmaDec *p, CLzma2Dec *l2, SizeT dicLimit, const Byte *src, Si
     st.l2_pack_left = l2->packSize; st.l2_unpack_left = l2->unpackSize;
     st.l2_flags = (l2->needInitDic ? 1u : 0u) | (l2->needInitState ? 2u : 0u) | (l2->needInitProp ? 4u : 0u);
   }
-  bool ok = lzb_cuda_ok(cudaMemcpy(ctl->d_state, &st, sizeof st, cudaMemcpyHostToDevice), "H2D state");
-  if (ok && prefix) ok = lzb_cuda_ok(cudaMemcpy(ctl->d_in, p->tempBuf, prefix, cudaMemcpyHostToDevice), "H2D held bytes");
-  if (ok && inSize) ok = lzb_cuda_ok(cudaMemcpy(ctl->d_in + prefix, src, inSize, cudaMemcpyHostToDevice), "H2D input");
-  if (!ok) return SZ_ERROR_FAIL;
-
-  LzbUnit u;
-  LzbResult x;
-  memset(&u, 0, sizeof u);
+  LzbUnit &u = *reinterpret_cast<LzbUnit *>(block);
+  memset(block, 0, LZB_STATEFUL_INPUT_AT);
   u.src_len = (uint32_t)total_in; u.dst_cap = (uint32_t)dicLimit; u.dict_size = p->prop.dicSize;
   u.codec = l2 ? LZB_CODEC_LZMA2 : LZB_CODEC_LZMA;
   u.lc = (uint8_t)mlc; u.lp = (uint8_t)mlp; u.pb = (uint8_t)mpb;      /* model sizing (LZMA2: worst case) */
@@ -183,12 +199,17 @@ static SRes step(CLzmaDec *p, CLzma2Dec *l2, SizeT dicLimit, const Byte *src, Si
   u.flags = LZB_UNIT_STATEFUL;
   u.filter_param = (uint32_t)p->dicBufSize;
   u.expect = (uint64_t)(uintptr_t)ctl->d_state;
-  SRes r = lzb_run_resident(c, ctl->d_in, ctl->d_dic, &u, &x, 1);
-  if (r != SZ_OK) return r;
+  if (prefix) memcpy(block + LZB_STATEFUL_INPUT_AT, p->tempBuf, prefix);
+  if (inSize) memcpy(block + LZB_STATEFUL_INPUT_AT + prefix, src, inSize);
+  memset(block + LZB_STATEFUL_INPUT_AT + total_in, 0, 16);
+
+  /* one queue, one wait: scalars + block up, launch, scalars + result + the first `guess` new dictionary bytes down */
   const SizeT old_pos = p->dicPos;
-  if (!lzb_cuda_ok(cudaMemcpy(&st, ctl->d_state, sizeof st, cudaMemcpyDeviceToHost), "D2H state")) return SZ_ERROR_FAIL;
-  if (st.dic_pos > old_pos &&
-      !lzb_cuda_ok(cudaMemcpy(p->dic + old_pos, ctl->d_dic + old_pos, st.dic_pos - old_pos, cudaMemcpyDeviceToHost), "D2H dictionary"))
+  const size_t guess = old_pos < dicLimit ? std::min<size_t>(dicLimit - old_pos, kDicGuessBytes) : 0;
+  SRes r = lzb_run_stateful(c, ctl->d_in, block, block_bytes, &u, ctl->d_state, &st, &x, ctl->d_dic, p->dic, old_pos, guess);
+  if (r != SZ_OK) return r;
+  if (st.dic_pos > old_pos + guess &&
+      !lzb_cuda_ok(cudaMemcpy(p->dic + old_pos + guess, ctl->d_dic + old_pos + guess, st.dic_pos - old_pos - guess, cudaMemcpyDeviceToHost), "D2H dictionary"))
     return SZ_ERROR_FAIL;
 
   /* scalars back into the reference's fields */

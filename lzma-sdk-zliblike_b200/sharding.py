@@ -12,7 +12,9 @@ import numpy as np
 
 
 def shard_bounds(dst_caps: np.ndarray, world: int) -> np.ndarray:
-    """world+1 unit indices; rank r owns units [b[r], b[r+1]).  Balanced by cumulative unpacked bytes."""
+    """world+1 unit indices; rank r owns units [b[r], b[r+1]).  Balanced by cumulative unpacked bytes.
+    The same rule as the C-ABI's Lzb_ShardBounds / Lzb_DecodeUnitsHostMulti (one process, several GPUs); checked
+    against it in tests/test_sharding_gloo.py."""
     n = len(dst_caps)
     if world <= 1 or n == 0:
         return np.array([0] + [n] * max(world, 1), dtype=np.int64)

@@ -22,7 +22,7 @@ extern "C" int emu_post_units(uint8_t *data, const LzbUnit *units, LzbResult *re
     const LzbUnit &u = units[i];
     LzbResult r;
     r.res = LZB_SZ_OK; r.status = LZB_ST_NOT_SPECIFIED; r.src_used = 0; r.dst_done = u.dst_cap; r.check = 0;
-    lzb::post_process<1, true>(u, r, data + u.dst_off, scratch.data(), scratch.data());
+    lzb::post_process<1, true>(u, r, data + u.dst_off, scratch.data(), scratch.data(), lzb::kPostScratchBytes);
     results[i] = r;
   }
   return 0;
@@ -56,7 +56,7 @@ static int decode_units(const uint8_t *packed, uint8_t *out, const LzbUnit *unit
       d.step();
     }
     d.finish_unit(r);
-    if (!stateful) lzb::post_process<1>(u, r, out + u.dst_off, (uint8_t *)probs.data(), (uint8_t *)matched.data());
+    if (!stateful) lzb::post_process<1>(u, r, out + u.dst_off, (uint8_t *)probs.data(), (uint8_t *)matched.data(), ns * 2);
     results[i] = r;
   }
   return 0;

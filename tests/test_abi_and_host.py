@@ -196,8 +196,8 @@ def test_few_units_launch_plan():
     assert (g.group, g.warps_per_cta, g.units_per_cta, g.smem_stride, g.ahead) == (16, 18, 36, 6448, 0)
     g = run(148 * 16 + 1)                           # one unit too many for a single wave of warps
     assert g.group == 16
-    g = run(2220)                                   # xz4m: 15 per SM, trees fit (15 x 14,640 B); too many warps to look ahead
-    assert (g.group, g.warps_per_cta, g.smem_stride, g.ahead) == (32, 15, 6448 + 8192, 0)
+    g = run(2220)                                   # xz4m: 15 per SM, trees fit (15 x 14,640 B); one unit per warp: look-ahead decoder
+    assert (g.group, g.warps_per_cta, g.smem_stride, g.ahead) == (32, 15, 6448 + 8192, 1)
     g = run(148 * 16)                               # 16 per SM: one warp each, trees stay in the slab
     assert (g.group, g.warps_per_cta, g.smem_stride) == (32, 16, 6448)
     g = run(1024)                                   # spread: 7 warps on every SM instead of 16 on 64; look-ahead decoder

@@ -267,6 +267,75 @@ def test_x86_convert_small_buffers_with_carried_state(gpu, ora):
     assert bad == 0
 
 
+def test_concurrent_one_call_decodes_are_combined_and_exact(gpu, ora):
+    """LzmaUncompress / LzmaDecode from many host threads at once: the calls share launches (lzb_host.cu, "callers that
+    do not batch") and every caller still gets exactly its own (SRes, destLen, srcLen) and bytes -- good streams,
+    truncated ones and short outputs mixed."""
+    import ctypes as C
+    import threading
+    L = lzb200.lib.load()
+    blobs, cs = cases.golden()
+    good = [c for c in cs if c["kind"] == "lzma" and c["mut"] is None and c["finish"] == 0 and c["cap"] > 0][:24]
+    jobs = []
+    for i, c in enumerate(good):
+        pk, props = blobs[c["blob"]], np.frombuffer(bytes.fromhex(c["props"]), np.uint8).copy()
+        variant = i % 3
+        src = pk if variant != 1 else pk[: max(6, len(pk) // 2)]
+        cap = c["cap"] if variant != 2 else max(1, c["cap"] // 3)
+        jobs.append((np.ascontiguousarray(src), props, cap, ora.lzma_decode(src, props, cap, 0)))
+    errors = []
+
+    def worker(k):
+        src, props, cap, want = jobs[k % len(jobs)]
+        for _ in range(6):
+            dst = np.zeros(cap + 8, np.uint8)
+            dl, sl = C.c_size_t(cap), C.c_size_t(len(src))
+            r = L.LzmaUncompress(dst.ctypes.data, C.byref(dl), src.ctypes.data, C.byref(sl), props.ctypes.data, 5)
+            if (r, dl.value, sl.value) != (want["res"], want["dest_len"], want["src_len"]) or \
+                    not np.array_equal(dst[: dl.value], want["out"][: dl.value]):
+                errors.append((k, r, dl.value, sl.value))
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(48)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors[:5]
+
+
+def test_one_table_over_several_contexts(gpu, ora):
+    """Lzb_DecodeUnitsHostMulti: one unit table cut over several contexts (here: several contexts of GPU 0 -- the
+    partition, the per-range arena windows and the threading are what is under test) == the single-context call."""
+    import ctypes as C
+    L = lzb200.lib.load()
+    L.Lzb_DecodeUnitsHostMulti.restype = C.c_int
+    L.Lzb_DecodeUnitsHostMulti.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
+    blobs, cs = cases.golden()
+    good = [c for c in cs if c["kind"] == "lzma" and c["mut"] is None and c["finish"] == 0 and c["cap"] > 0]
+    props0 = good[0]["props"]
+    good = [c for c in good if c["props"] == props0] * 9
+    n = len(good)
+    plen = np.array([len(blobs[c["blob"]]) for c in good], dtype=np.uint64)
+    ulen = np.array([c["cap"] for c in good], dtype=np.uint64)
+    soff = np.concatenate(([0], np.cumsum((plen + 15) & ~np.uint64(15))[:-1])).astype(np.uint64)
+    doff = np.concatenate(([0], np.cumsum(ulen)[:-1])).astype(np.uint64)
+    packed = np.zeros(int(soff[-1] + plen[-1]) + 64, np.uint8)
+    for i, c in enumerate(good):
+        packed[int(soff[i]):int(soff[i]) + int(plen[i])] = blobs[c["blob"]]
+    units = lzb200.sdk.raw_lzma_units(soff, plen.astype(np.uint32), doff, ulen.astype(np.uint32), bytes.fromhex(props0))
+    ctxs = [lzb200.lib.Context(0) for _ in range(3)]
+    one = np.zeros(int(doff[-1] + ulen[-1]) + 64, np.uint8)
+    r1 = lzb200.sdk.decode_units_host(ctxs[0], packed, one, units)
+    for k in (2, 3):
+        out = np.zeros_like(one)
+        res = np.zeros(n, dtype=R.RESULT_DTYPE)
+        arr = (C.c_void_p * k)(*[c.h for c in ctxs[:k]])
+        rc = L.Lzb_DecodeUnitsHostMulti(arr, k, packed.ctypes.data, packed.size, out.ctypes.data, out.size, units.ctypes.data, res.ctypes.data, n)
+        assert rc == 0 and np.array_equal(res, r1)
+        for j in range(n):                      # (bytes behind a unit's dst_done are not part of the contract)
+            o, m = int(doff[j]), int(res["dst_done"][j])
+            assert np.array_equal(out[o:o + m], one[o:o + m]), (k, j)
+    for c in ctxs:
+        c.close()
+
+
 def test_golden_lzma86_one_call(gpu):
     """Lzma86_Decode / Lzma86_GetUnpackSize (Lzma86Dec.c) vs the reference's answers: tests/golden/lzma86.json."""
     import json

@@ -37,6 +37,22 @@ def test_bounds_cover_and_balance():
     assert np.diff(shard_bounds(u["dst_cap"], 8)).tolist() == [512] * 8
 
 
+def test_c_abi_shard_bounds_is_the_same_rule():
+    """Lzb_ShardBounds (what Lzb_DecodeUnitsHostMulti uses for the GPUs of one process) == sharding.shard_bounds
+    (what one-process-per-GPU hosts use).  Host arithmetic only: the library loads without a device."""
+    import ctypes as C
+    L = lzb200.lib.load()
+    L.Lzb_ShardBounds.restype = None
+    L.Lzb_ShardBounds.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    for n, world in ((1000, 2), (1000, 8), (7, 8), (1, 4), (0, 2), (65536, 8), (8192, 8), (8192, 3)):
+        u = _table(n, 3 * n + world)
+        if n == 8192:
+            u["dst_cap"] = 1 << 20
+        b = np.zeros(world + 1, dtype=np.uint64)
+        L.Lzb_ShardBounds(u.ctypes.data, n, world, b.ctypes.data)
+        assert b.astype(np.int64).tolist() == shard_bounds(u["dst_cap"], world).tolist(), (n, world)
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))

@@ -182,3 +182,20 @@ def test_gpu_match_of_len_eq_distance_at_the_ring_wrap(ref):
             b = g.lzma_decode_tobuf(packed, props, len(plain), ic, oc, 0)
             same(a, b)
             assert np.array_equal(b["out"][: len(plain)], plain)
+
+
+@pytest.mark.gpu
+@pytest.mark.needref
+def test_gpu_config1_at_baseline_size(ref):
+    """BASELINE configs[0] at size: ONE 64 MiB stream, lc3 lp0 pb2, 16 MiB dictionary (the ring wraps three times),
+    through LzmaDec_Allocate + LzmaDec_DecodeToBuf fed 64 KiB in / 64 KiB out like LzmaUtil.c:55-106 -- same
+    (SRes, status, destLen, srcLen) and bytes as the reference's own loop.  One stream = one warp: ~15 s on a B200."""
+    import zlib
+    from tools.corpus import make_corpus
+    plain = make_corpus(64 << 20, seed=4321)
+    packed, props = ref.lzma_encode(plain, level=1, dict_size=16 << 20, end_mark=1)
+    a = ref.lzma_decode_tobuf(packed, props, len(plain), 1 << 16, 1 << 16, 0)
+    b = GpuStream().lzma_decode_tobuf(packed, props, len(plain), 1 << 16, 1 << 16, 0)
+    for f in ("res", "status", "dest_len", "src_len"):
+        assert a[f] == b[f], f
+    assert zlib.crc32(b["out"][: len(plain)].tobytes()) == zlib.crc32(plain.tobytes())

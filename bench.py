@@ -634,7 +634,18 @@ def main():
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the first communicator comes up; stdout carries the ONE JSON
+        # line of the contract, so the banner goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     ctx = lzb200.lib.Context(local)
     env = dict(rank=rank, world=world, local=local, dist=dist, cache=cache, dev=torch.device("cuda", local), ctx=ctx, small=a.small)
 

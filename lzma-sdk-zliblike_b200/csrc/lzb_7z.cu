@@ -12,7 +12,7 @@
  * The result codes are the reference's: what SzArEx_Open returns for a damaged database, and per file what
  * SzArEx_Extract returns (folder decode error, folder CRC, file CRC).  BCJ2 folders (7zDec.c:308-329: three
  * coders feeding a four-stream merge) decode their three streams as ordinary units and merge on the device
- * (lzb_bcj2_kernel, one thread per folder).  PPMd (disabled in the reference) is SZ_ERROR_UNSUPPORTED.
+ * (lzb_bcj2_kernel, one warp per folder).  PPMd (disabled in the reference) is SZ_ERROR_UNSUPPORTED.
  */
 #include "lzb_host.h"
 #include "lzb_xz.h"

@@ -628,6 +628,10 @@ template <uint32_t G, bool kSmem = false, bool kAhead = false> struct UnitDecode
         if (BITS > 6 && i == 4) top_up();
         const uint32_t A0 = A * 2 - L;                   /* child 0; child 1 is the next entry */
         const uint32_t pair = (i + 1 < BITS) ? ldp32(A0) : 0u;
+        /* (a version of this step shaped for a shorter chain -- (range >> 11) picked from two shifts that do not wait for
+         * the normalisation, both probability updates computed ahead of the compare: +4 instructions -- ran 2-9 % SLOWER
+         * at 1, 7, 14 and 15 warps per SM: a warp issues about one instruction per four cycles whatever their
+         * dependences, so the count is what matters here too; profiles/r02_kernel_log.md G) */
         rc_norm();
         uint32_t np, nA, npr;
         bit_math2(pr, A0, A0 + 2, pair & 0xFFFFu, pair >> 16, np, nA, npr);

@@ -1120,7 +1120,7 @@ extern "C" SRes Lzma86_Decode(Byte *dest, SizeT *destLen, const Byte *src, SizeT
 }
 
 /* ------------------------------------------------------------------ BCJ2 merge, stand-alone ---------- */
-/* reference Bcj2.c:28-127 (Bcj2.h:24-30): the four streams go to the device, one thread merges them */
+/* reference Bcj2.c:28-127 (Bcj2.h:24-30): the four streams go to the device, one warp merges them */
 extern "C" int Bcj2_Decode(const Byte *buf0, SizeT size0, const Byte *buf1, SizeT size1, const Byte *buf2, SizeT size2,
                            const Byte *buf3, SizeT size3, Byte *outBuf, SizeT outSize)
 {

@@ -171,10 +171,18 @@ lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict_
     }
     if (__all_sync(0xffffffffu, d.st == S_EXIT)) break;
     /* hot loop: one symbol per unit and trip, until some unit of the warp needs the driver again */
-    do
+    if (kAhead)
     {
-      if (d.st == S_RUN) d.step();
-    } while (!__any_sync(0xffffffffu, d.st != S_RUN && d.st != S_EXIT));
+      /* one unit per warp: every lane holds the same state, the loop test is uniform without asking the warp */
+      while (d.st == S_RUN) d.step();
+    }
+    else
+    {
+      do
+      {
+        if (d.st == S_RUN) d.step();
+      } while (!__any_sync(0xffffffffu, d.st != S_RUN && d.st != S_EXIT));
+    }
   }
 }
 

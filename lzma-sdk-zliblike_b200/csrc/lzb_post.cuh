@@ -175,6 +175,7 @@ template <uint32_t G> LZB_FN void delta_decode_group(uint8_t *data, uint32_t siz
 LZB_FN uint32_t mulmod32(uint32_t a, uint32_t b)
 {
   uint32_t p = 0;
+#pragma unroll 1                       /* cold (once per unit and lane): keep it small, the kernel it is inlined into is hot */
   for (int k = 0; k < 32; k++)
   {
     p ^= b & (0u - ((a >> (31 - k)) & 1));
@@ -185,6 +186,7 @@ LZB_FN uint32_t mulmod32(uint32_t a, uint32_t b)
 LZB_FN uint64_t mulmod64(uint64_t a, uint64_t b)
 {
   uint64_t p = 0;
+#pragma unroll 1
   for (int k = 0; k < 64; k++)
   {
     p ^= b & (0ull - ((a >> (63 - k)) & 1));
@@ -196,12 +198,14 @@ LZB_FN uint64_t mulmod64(uint64_t a, uint64_t b)
 LZB_FN uint32_t xpow32(uint32_t n)
 {
   uint32_t r = 1u << 31, sq = 1u << 23;
+#pragma unroll 1
   for (; n != 0; n >>= 1) { if (n & 1) r = mulmod32(r, sq); sq = mulmod32(sq, sq); }
   return r;
 }
 LZB_FN uint64_t xpow64(uint32_t n)
 {
   uint64_t r = 1ull << 63, sq = 1ull << 55;
+#pragma unroll 1
   for (; n != 0; n >>= 1) { if (n & 1) r = mulmod64(r, sq); sq = mulmod64(sq, sq); }
   return r;
 }
@@ -224,9 +228,11 @@ template <uint32_t G, class T> LZB_FN void crc_tables(T *table, T poly, uint32_t
   typedef Group<G> Grp;
   const uint32_t lane = Grp::lane();
   Grp::sync();
+#pragma unroll 1
   for (uint32_t i = lane; i < 256; i += G)
   {
     T r = (T)i;
+#pragma unroll 1
     for (int k = 0; k < 8; k++) r = (r >> 1) ^ (poly & (T)(0 - (r & 1)));
     table[i] = r;
   }

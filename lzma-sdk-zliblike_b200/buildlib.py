@@ -36,7 +36,11 @@ def build(force: bool = False, verbose: bool = False, variant: str | None = None
     """Compile (if needed) and return the path of liblzb200.so.
 
     variant: build an A/B copy of the library into lib/variants/<variant>/ with extra nvcc flags (kernel
-    experiments; selected at run time with LZB_LIB=<path>).  The shipped library is built without any."""
+    experiments; selected at run time with LZB_LIB=<path>).  The shipped library is built without any.
+
+    Safe against several processes calling it at once (one rank per GPU under torchrun): the build happens under an
+    exclusive file lock, into a private directory, and the finished library is moved into place atomically -- a
+    process never sees a half-written file, and whoever comes second finds the library fresh."""
     if variant is None and os.environ.get("LZB_LIB"):
         return os.environ["LZB_LIB"]                    # an A/B build chosen for this process (tools/build_variant.py)
     if variant is None and not force and not _stale():
@@ -44,23 +48,35 @@ def build(force: bool = False, verbose: bool = False, variant: str | None = None
     libdir = LIBDIR if variant is None else os.path.join(LIBDIR, "variants", variant)
     so = os.path.join(libdir, "liblzb200.so")
     os.makedirs(libdir, exist_ok=True)
-    nvcc = _nvcc()
-    objs, cmds = [], []
-    for src in SOURCES:
-        obj = os.path.join(libdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-            print(" ".join(cmd))
-        cmds.append(cmd)
-        objs.append(obj)
-    procs = [subprocess.Popen(c) for c in cmds]          # the translation units are independent: compile them side by side
-    for c, p in zip(cmds, procs):
-        if p.wait() != 0:
-            raise subprocess.CalledProcessError(p.returncode, c)
-    cmd = [nvcc, "-shared", "-o", so, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xlinker", "-Bsymbolic", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
-    subprocess.check_call(cmd)
+    import fcntl
+    import tempfile
+    with open(os.path.join(libdir, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if variant is None and not force and not _stale():
+            return so                                   # another process built it while this one waited
+        nvcc = _nvcc()
+        work = tempfile.mkdtemp(prefix=".build-", dir=libdir)
+        try:
+            objs, cmds = [], []
+            for src in SOURCES:
+                obj = os.path.join(work, src.replace(".cu", ".o"))
+                cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
+                    print(" ".join(cmd))
+                cmds.append(cmd)
+                objs.append(obj)
+            procs = [subprocess.Popen(c) for c in cmds]      # the translation units are independent: side by side
+            for c, p in zip(cmds, procs):
+                if p.wait() != 0:
+                    raise subprocess.CalledProcessError(p.returncode, c)
+            tmp_so = os.path.join(work, "liblzb200.so")
+            cmd = [nvcc, "-shared", "-o", tmp_so, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+                   "-Xlinker", "-Bsymbolic", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+            subprocess.check_call(cmd)
+            os.replace(tmp_so, so)
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
     return so
 
 

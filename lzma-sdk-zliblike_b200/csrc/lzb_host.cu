@@ -1080,16 +1080,73 @@ static bool gpu_filter(Byte *data, size_t size, int filter, uint32_t param, uint
   return ok;
 }
 
+/* A large buffer is cut into SEGMENTS that other warps can convert at the same time.  A segment may start at p when
+ * none of the four bytes in front of p is an E8 / E9 opcode candidate: the converter's 3-bit history is provably zero
+ * there and no conversion in front of p writes at or behind p (the same argument that lets the 32 lanes of a warp split
+ * a buffer, lzb_post.cuh) -- so segment by segment gives byte for byte what one sequential pass gives.  The cut points
+ * are found here on the host copy (a few bytes around each nominal boundary).  Every segment but the last is handed
+ * over with four extra bytes so that its candidates run right up to the next segment's start. */
+static const size_t kX86SegmentBytes = (size_t)1 << 16;
+
+static bool x86_segments(const Byte *data, size_t size, std::vector<size_t> &starts)
+{
+  starts.assign(1, 0);
+  if (size < 4 * kX86SegmentBytes) return false;
+  for (size_t nominal = kX86SegmentBytes; nominal + kX86SegmentBytes <= size; nominal += kX86SegmentBytes)
+  {
+    size_t p = std::max(nominal, starts.back() + 8), clean = 0;
+    for (size_t q = p - 4; q < p; q++) clean = (data[q] & 0xFE) == 0xE8 ? 0 : clean + 1;
+    while (clean < 4 && p + 8 < size) { clean = (data[p] & 0xFE) == 0xE8 ? 0 : clean + 1; p++; }
+    if (clean < 4 || p + 8 >= size) break;                 /* (a buffer that is nothing but candidates: fewer segments) */
+    starts.push_back(p);
+  }
+  return starts.size() > 1;
+}
+
 extern "C" SizeT x86_Convert(Byte *data, SizeT size, UInt32 ip, UInt32 *state, int encoding)
 {
   /* reference Bra86.c:11-85: both directions, history carried in *state, returns the bytes processed.
-   * One warp scans the buffer in 32 segments that start at history-free positions (lzb_post.cuh). */
+   * One warp scans a segment in 32 pieces that start at history-free positions (lzb_post.cuh). */
   if (size < 5) return 0;
-  LzbResult r;
   const uint8_t flags = (uint8_t)(4 | (encoding ? 2 : 0));
-  if (!gpu_filter(data, size, LZB_FILTER_X86, ip, flags, (uint64_t)(*state & 7) << 32, &r)) return 0;
-  *state = (UInt32)r.status;
-  return r.src_used;
+  std::vector<size_t> starts;
+  if (size > 0xFFFFFFFFull || !x86_segments(data, size, starts))
+  {
+    LzbResult r;
+    if (!gpu_filter(data, size, LZB_FILTER_X86, ip, flags, (uint64_t)(*state & 7) << 32, &r)) return 0;
+    *state = (UInt32)r.status;
+    return r.src_used;
+  }
+  LzbContext *c = lzb_default_context();
+  if (!c) return 0;
+  const size_t n = starts.size();
+  std::vector<LzbUnit> units(n);
+  std::vector<LzbResult> results(n);
+  for (size_t i = 0; i < n; i++)
+  {
+    LzbUnit &u = units[i];
+    memset(&u, 0, sizeof u);
+    const size_t end = i + 1 < n ? starts[i + 1] + 4 : size;
+    u.dst_off = starts[i]; u.dst_cap = (uint32_t)(end - starts[i]);
+    u.filter = LZB_FILTER_X86; u.filter_param = ip + (UInt32)starts[i];
+    u.flags = flags;
+    u.expect = i == 0 ? (uint64_t)(*state & 7) << 32 : 0;
+  }
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!lzb_cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return 0;
+  LzbSlot &s = c->slot[0];
+  if (!lzb_slot_reserve(c, s, 0, size, n, 0)) return 0;
+  bool ok = lzb_cuda_ok(cudaMemcpyAsync(s.d_out, data, size, cudaMemcpyHostToDevice, s.stream), "H2D data") &&
+            lzb_cuda_ok(cudaMemcpyAsync(s.d_units, units.data(), n * sizeof(LzbUnit), cudaMemcpyHostToDevice, s.stream), "H2D units");
+  if (!ok) return 0;
+  const int rc = lzb_launch_post_only(s.d_out, s.d_units, s.d_results, (uint32_t)n, s.stream);
+  if (rc != 0) { lzb_set_error("post launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return 0; }
+  ok = lzb_cuda_ok(cudaMemcpyAsync(data, s.d_out, size, cudaMemcpyDeviceToHost, s.stream), "D2H data") &&
+       lzb_cuda_ok(cudaMemcpyAsync(results.data(), s.d_results, n * sizeof(LzbResult), cudaMemcpyDeviceToHost, s.stream), "D2H results") &&
+       lzb_cuda_ok(cudaStreamSynchronize(s.stream), "filter kernel");
+  if (!ok) return 0;
+  *state = (UInt32)results[n - 1].status;
+  return starts[n - 1] + results[n - 1].src_used;
 }
 
 /* ------------------------------------------------------------------ LZMA + x86 one-call form -------- */

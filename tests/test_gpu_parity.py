@@ -240,6 +240,13 @@ def test_filters_and_checks_large(gpu, ora):
     for enc in (0, 1):
         a, b = ora.x86_convert(data, 0, 0, enc), gpu.x86_convert(data, 0, 0, enc)
         assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+    # large buffers are cut into segments converted by different warps (lzb_host.cu): carried state, odd sizes, a
+    # start offset, and data that is nothing but opcode candidates (no place to cut)
+    dense = np.full(600_000, 0xE8, np.uint8)
+    for buf, ip, st, enc in ((data[:1_000_003], 0x40001000, 5, 0), (data[7:2_500_000], 12345, 3, 1), (dense, 0, 1, 0),
+                             (np.concatenate((dense[:300_000], data[:400_000])), 0x7FFFFFF0, 0, 0)):
+        a, b = ora.x86_convert(buf, ip, st, enc), gpu.x86_convert(buf, ip, st, enc)
+        assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], (len(buf), ip, st, enc, a[1:], b[1:])
     for dist in (1, 2, 3, 4, 33, 256):
         assert np.array_equal(ora.delta(data, dist, 0), gpu.delta(data, dist))
     # carried history across two Delta_Decode calls == one call

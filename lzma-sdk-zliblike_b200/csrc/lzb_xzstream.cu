@@ -506,10 +506,10 @@ static void block_payload_done(CXzUnpacker *p)
   n += Xz_WriteVarInt(rec + n, p->unpackSize);
   sha_absorb(&p->sha, rec, n, false);
   p->indexSize += n;
-  p->numBlocks++;
+  p->numBlocks += 1;
+  p->alignPos = 0;
   p->state = XZ_STATE_BLOCK_FOOTER;
   p->pos = 0;
-  p->alignPos = 0;
 }
 
 /* ---- container framing (xz format 2.1 stream, 3.1 block header, 3.3 padding, 3.4 check, 4 index, 2.1.2 footer,
@@ -567,6 +567,13 @@ Pending pending_of(const CXzUnpacker *p)
   }
 }
 
+/* move to another part of the container; every part starts with its byte counter at zero */
+void enter(CXzUnpacker *p, EXzState part)
+{
+  p->state = part;
+  p->pos = 0;
+}
+
 void keep(CXzUnpacker *p, const Byte *src, size_t n)
 {
   memcpy(p->buf + p->pos, src, n);
@@ -576,13 +583,14 @@ void keep(CXzUnpacker *p, const Byte *src, size_t n)
 /* the index of a stream starts with bytes the decoder can predict: 0x00 and the number of blocks it has seen */
 void index_begins(CXzUnpacker *p)
 {
-  p->indexPreSize = 1 + Xz_WriteVarInt(p->buf + 1, p->numBlocks);
-  p->indexPos = p->indexPreSize;
-  p->indexSize += p->indexPreSize;
-  Sha256_Final(&p->sha, p->shaDigest);                   /* digest of the records the blocks implied */
-  Sha256_Init(&p->sha);                                  /* ... against the records that are stored    */
-  p->crc = lzb_small_crc32_update(0xFFFFFFFFu, p->buf, p->indexPreSize);
-  p->state = XZ_STATE_STREAM_INDEX;
+  const unsigned head = 1u + Xz_WriteVarInt(&p->buf[1], p->numBlocks);
+  p->indexPreSize = head;
+  p->indexPos = head;
+  p->indexSize += head;
+  Sha256_Final(&p->sha, &p->shaDigest[0]);               /* digest of the records the blocks implied */
+  lzb::sha256_init(p->sha.state); p->sha.count = 0;      /* ... against the records that are stored    */
+  p->crc = lzb_small_crc32_update(0xFFFFFFFFu, p->buf, head);
+  p->state = XZ_STATE_STREAM_INDEX;                      /* (pos stays 1: the indicator byte is the head's first) */
 }
 
 /* absorb up to n (<= want.bytes, <= what the caller has) bytes of the element being read */
@@ -603,7 +611,7 @@ SRes frame_feed(CXzUnpacker *p, Pending want, const Byte *src, size_t n, size_t 
       keep(p, src, 1);
       *used = 1;
       if (src[0] == 0) index_begins(p);
-      p->blockHeaderSize = ((UInt32)p->buf[0] << 2) + 4;
+      p->blockHeaderSize = 4u * ((UInt32)src[0] + 1u);
       return SZ_OK;
     case EL_BLOCK_HEADER:
     case EL_BLOCK_CHECK:
@@ -647,8 +655,8 @@ SRes frame_feed(CXzUnpacker *p, Pending want, const Byte *src, size_t n, size_t 
       keep(p, src, n);
       *used = n;
       if (p->pos != kStreamFooterBytes) return SZ_OK;
-      p->state = XZ_STATE_STREAM_PADDING;
-      p->numStreams++;
+      p->state = XZ_STATE_STREAM_PADDING;                /* (pos keeps the footer's 12: padding counts in padSize) */
+      p->numStreams += 1;
       p->padSize = 0;
       const Byte *f = p->buf;
       const bool good = lzb_le32(f) == lzb_small_crc32(f + 4, 6) &&
@@ -660,8 +668,7 @@ SRes frame_feed(CXzUnpacker *p, Pending want, const Byte *src, size_t n, size_t 
       if (src[0] == 0) { p->padSize++; *used = 1; return SZ_OK; }
       /* something else begins here: only on a four-byte boundary, and it is not consumed by this element */
       if (((UInt32)p->padSize & 3) != 0) return SZ_ERROR_NO_ARCHIVE;
-      p->pos = 0;
-      p->state = XZ_STATE_STREAM_HEADER;
+      enter(p, XZ_STATE_STREAM_HEADER);
       return SZ_OK;
   }
   return SZ_ERROR_FAIL;
@@ -676,21 +683,17 @@ SRes frame_close(CXzUnpacker *p, Element el)
     {
       const SRes r = Xz_ParseHeader(&p->streamFlags, p->buf);
       if (r != SZ_OK) return r;
-      Sha256_Init(&p->sha);
-      p->indexSize = 0;
-      p->numBlocks = 0;
-      p->pos = 0;
-      p->state = XZ_STATE_BLOCK_HEADER;
+      lzb::sha256_init(p->sha.state); p->sha.count = 0;
+      p->indexSize = p->numBlocks = 0;
+      enter(p, XZ_STATE_BLOCK_HEADER);
       return SZ_OK;
     }
     case EL_BLOCK_HEADER:
     {
       SRes r = XzBlock_Parse(&p->block, p->buf);
       if (r != SZ_OK) return r;
-      p->state = XZ_STATE_BLOCK;
-      p->pos = 0;                                        /* (this library's own marker lives here while in BLOCK) */
-      p->packSize = 0;
-      p->unpackSize = 0;
+      enter(p, XZ_STATE_BLOCK);                          /* (this library's own marker lives in pos while in BLOCK) */
+      p->packSize = p->unpackSize = 0;
       XzCheck_Init(&p->check, p->streamFlags & 0xF);
       return XzDec_Init(&p->decoder, &p->block);
     }
@@ -698,22 +701,19 @@ SRes frame_close(CXzUnpacker *p, Element el)
     {
       Byte digest[LZB_XZ_CHECK_SIZE_MAX];
       const UInt32 n = XzFlags_GetCheckSize(p->streamFlags);
-      p->state = XZ_STATE_BLOCK_HEADER;
-      p->pos = 0;
+      enter(p, XZ_STATE_BLOCK_HEADER);
       return (XzCheck_Final(&p->check, digest) && memcmp(digest, p->buf, n) != 0) ? SZ_ERROR_CRC : SZ_OK;
     }
     case EL_INDEX_PAD:
     {
-      Byte digest[SHA256_DIGEST_SIZE];
-      p->state = XZ_STATE_STREAM_INDEX_CRC;
-      p->indexSize += 4;
-      p->pos = 0;
-      Sha256_Final(&p->sha, digest);
-      return memcmp(digest, p->shaDigest, SHA256_DIGEST_SIZE) != 0 ? SZ_ERROR_CRC : SZ_OK;
+      Byte stored[SHA256_DIGEST_SIZE];
+      enter(p, XZ_STATE_STREAM_INDEX_CRC);
+      p->indexSize += 4;                                 /* the CRC32 that follows belongs to the index's size */
+      Sha256_Final(&p->sha, stored);
+      return memcmp(stored, p->shaDigest, SHA256_DIGEST_SIZE) != 0 ? SZ_ERROR_CRC : SZ_OK;
     }
     case EL_INDEX_CRC:
-      p->state = XZ_STATE_STREAM_FOOTER;
-      p->pos = 0;
+      enter(p, XZ_STATE_STREAM_FOOTER);
       return (p->crc ^ 0xFFFFFFFFu) != lzb_le32(p->buf) ? SZ_ERROR_CRC : SZ_OK;
     default:
       return SZ_ERROR_FAIL;                              /* the other elements are never "complete and pending" */

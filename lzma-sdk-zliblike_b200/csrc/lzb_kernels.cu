@@ -128,6 +128,9 @@ lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict_
     if (d.st == S_FETCH)
     {
       uint32_t i = 0;
+      /* (tried: once fewer units than warps are left, only the first group of a warp takes units -- at most one unit per
+       * warp in the tail.  Slower: 7.46 vs 7.52 GB/s at 8,192 units, 7.85 vs 8.25 at two full waves: an empty slot costs
+       * more than two units sharing a warp; profiles/r02_kernel_log.md K) */
       if (Grp::lane() == 0) i = atomicAdd(ticket, 1u);
       i = Grp::bcast(i, 0);
       if (i >= n_units) d.st = S_EXIT;
@@ -407,7 +410,12 @@ extern "C" void lzb_plan_few_units(LzbGeometry *gp, uint32_t n_units, size_t sme
   if (g.shared_model && g.group < 32 && regroup_allowed)
   {
     const uint32_t w32 = g.units_per_cta < lzb::max_warps_for(32) ? g.units_per_cta : lzb::max_warps_for(32);
-    if (n_units <= g.ctas * w32)
+    /* ... and a little beyond one wave: up to ~29 units per SM the look-ahead form with 16 persistent warps (units
+     * taken from the ticket as warps come free) still beats two units per warp at partial residency -- 5.15 vs 4.74
+     * GB/s at 3,072 units of 1 MiB, 6.41 vs 6.19 at 4,096; at 5,328 (36 per SM) the dense form wins 8.08 to 6.19
+     * (profiles/r02_kernel_log.md J) */
+    const uint32_t dense_from = (g.units_per_cta * 29u) / 36u;          /* units per SM where the dense form takes over */
+    if (n_units <= g.ctas * w32 || (w32 == lzb::max_warps_for(32) && n_units <= g.ctas * dense_from))
     {
       g.group = 32;
       g.warps_per_cta = w32;

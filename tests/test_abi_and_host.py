@@ -188,14 +188,18 @@ def test_few_units_launch_plan():
         assert g.units_per_cta * g.smem_stride <= optin                   # the launch fits in shared memory
         assert g.smem_stride in (g.region_bytes, g.region_bytes + g.slab_stride)
         if g.group == 32:
-            assert g.ctas * g.units_per_cta >= n                          # one wave: a warp for every unit
+            assert g.ctas * g.units_per_cta >= n or g.warps_per_cta == 16 # one wave, or 16 persistent warps per SM
             assert g.units_per_cta * g.ctas * g.slab_stride <= g.slab_bytes   # inside the slab sized for the default
         return g
 
     g = run(65536)                                  # the bench batch: throughput mode untouched
     assert (g.group, g.warps_per_cta, g.units_per_cta, g.smem_stride, g.ahead) == (16, 18, 36, 6448, 0)
-    g = run(148 * 16 + 1)                           # one unit too many for a single wave of warps
-    assert g.group == 16
+    g = run(148 * 16 + 1)                           # a little more than one wave of warps: still one unit per warp, persistent
+    assert (g.group, g.warps_per_cta, g.ahead) == (32, 16, 1)
+    g = run(148 * 29)
+    assert (g.group, g.warps_per_cta) == (32, 16)
+    g = run(148 * 29 + 1)                           # from here on two units per warp
+    assert (g.group, g.warps_per_cta, g.ahead) == (16, 18, 0)
     g = run(2220)                                   # xz4m: 15 per SM, trees fit (15 x 14,640 B); one unit per warp: look-ahead decoder
     assert (g.group, g.warps_per_cta, g.smem_stride, g.ahead) == (32, 15, 6448 + 8192, 1)
     g = run(148 * 16)                               # 16 per SM: one warp each, trees stay in the slab

@@ -20,16 +20,23 @@
  *                   What a plain symbol touches -- 950 fixed + (56 << pb) + the 256-entry plain-literal tree
  *                   of every context -- lives in shared memory (6,448 B at lc3 lp0 pb2); the 512-entry
  *                   matched-literal trees (used only right after a match) live in an L2-resident HBM slab.
- *   packed input  : consumed through a 4-byte register window refilled by aligned 32-bit loads, the next
- *                   word prefetched one refill ahead (the bit loop never waits on HBM).
+ *   packed input  : consumed through a register window refilled by aligned 32-bit loads, the next word prefetched
+ *                   one refill ahead (the bit loop never waits on HBM).
  *   window/output : the unit's slice of the output arena in HBM *is* the dictionary (dic = dest,
  *                   LzmaDec.c:988-989); literals are stored by the group's lane 0, matches copied by G lanes.
  *                   The two bytes the next literal can depend on (previous byte, match byte) are fetched
  *                   when the match is issued, so no literal waits on a window load.
  *
+ * Two forms of the symbol decoder (UnitDecoderT<G, kSmem, kAhead>; DESIGN.md 4a, profiles/r02_kernel_log.md):
+ *   lean       (kAhead = false, lzb_core_lean.inc)  dense launches, two units per warp: fewest issued instructions
+ *              (normalisation = a rarely taken branch, 4-byte window)
+ *   look-ahead (kAhead = true, this file)           one unit per warp: predicated normalisation over an 8-byte window,
+ *              both children of a tree node loaded while the node's bit is decided
+ * Everything around the symbol (driver machine, window copies, model init, state save / load) is shared.
+ *
  * Semantics restated from the reference (cited per function): LzmaDec.c / Lzma2Dec.c.  The same source
  * compiles for the host with -DLZB_EMU (tests/emu): a TEST-ONLY emulation with G = 1 used to exercise this
- * logic on machines without a GPU.  The product library never contains that build.
+ * logic -- both forms -- on machines without a GPU.  The product library never contains that build.
  */
 #pragma once
 

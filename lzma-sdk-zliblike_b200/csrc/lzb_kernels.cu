@@ -11,6 +11,8 @@
  * plain symbol touches lives in shared memory (6,448 B at lc3/lp0/pb2 -> 36 fit); the matched-literal trees
  * (8 KiB, touched once per match) live in an L2-resident HBM slab.  With K units
  * per warp only units/K warps need registers: the default is G = 16, 18 warps, 36 units per SM.
+ * Launches with at most 29 units per SM run one unit per warp (G = 32) in the look-ahead form of the decoder
+ * (lzb_plan_few_units; up to 16 per SM one wave spread over all SMs, beyond that 16 persistent warps per SM).
  * Models whose shared part exceeds 56 KiB (raw LZMA with lc+lp >= 6) live entirely in the slab.
  *
  * Streaming.  The <..., kFlow = true> instantiation is the same loop for a launch that is fed and drained while

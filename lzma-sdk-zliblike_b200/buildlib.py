@@ -23,13 +23,25 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: liblzb200.so cannot be built (there is no CPU fallback)")
 
 
-def _stale() -> bool:
-    if not os.path.exists(SO):
-        return True
-    t = os.path.getmtime(SO)
+def _source_digest(extra_flags=()) -> str:
+    """What the library is made of: every file of csrc/, the public header and the compiler flags."""
+    import hashlib
+    h = hashlib.sha256()
     inc = os.path.join(os.path.dirname(HERE), "include", "lzb200.h")
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [inc]
-    return any(os.path.getmtime(d) > t for d in deps)
+    for path in sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [inc]:
+        h.update(os.path.basename(path).encode())
+        h.update(open(path, "rb").read())
+    h.update(" ".join([*NVCC_FLAGS, *extra_flags]).encode())
+    return h.hexdigest()
+
+
+def _stale() -> bool:
+    """By content, not by time stamps: a copy of the tree (the GPU box gets one) keeps a library that matches its
+    sources whatever the copy did to the mtimes."""
+    stamp = SO + ".src"
+    if not os.path.exists(SO) or not os.path.exists(stamp):
+        return True
+    return open(stamp).read().strip() != _source_digest()
 
 
 def build(force: bool = False, verbose: bool = False, variant: str | None = None, extra_flags=()) -> str:
@@ -75,6 +87,8 @@ def build(force: bool = False, verbose: bool = False, variant: str | None = None
                    "-Xlinker", "-Bsymbolic", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
             subprocess.check_call(cmd)
             os.replace(tmp_so, so)
+            with open(so + ".src", "w") as f:
+                f.write(_source_digest(extra_flags) + "\n")
         finally:
             shutil.rmtree(work, ignore_errors=True)
     return so

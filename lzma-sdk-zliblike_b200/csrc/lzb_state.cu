@@ -258,28 +258,41 @@ extern "C" SRes LzmaDec_DecodeToDic(CLzmaDec *p, SizeT dicLimit, const Byte *src
   return step(p, nullptr, dicLimit, src, srcLen, finishMode, status, "LzmaDec_DecodeToDic");
 }
 
+/* The buffer interface over the dictionary interface (reference LzmaDec.c:840-878, Lzma2Dec.c:291-328): the decoder
+ * writes into its ring dictionary, every slice it produces is copied out to the caller.  A slice ends where the ring
+ * ends or where the caller's buffer ends; only the second is an end the caller's finish mode applies to. */
+template <class ToDic>
+static SRes decode_to_buf(CLzmaDec *d, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
+                          ELzmaFinishMode finishMode, ELzmaStatus *status, ToDic to_dic)
+{
+  Byte *out = dest, *const out_end = dest + *destLen;
+  const Byte *in = src, *const in_end = src + *srcLen;
+  SRes res;
+  for (;;)
+  {
+    if (d->dicPos == d->dicBufSize) d->dicPos = 0;                      /* the ring wraps */
+    const SizeT from = d->dicPos;
+    const SizeT wanted = (SizeT)(out_end - out), ring_left = d->dicBufSize - from;
+    const bool to_callers_end = wanted <= ring_left;
+    SizeT used = (SizeT)(in_end - in);
+    res = to_dic(to_callers_end ? from + wanted : d->dicBufSize, in, &used, to_callers_end ? finishMode : LZMA_FINISH_ANY, status);
+    in += used;
+    const SizeT made = d->dicPos - from;
+    memcpy(out, d->dic + from, made);
+    out += made;
+    if (res != SZ_OK || made == 0 || out == out_end) break;
+  }
+  *destLen = (SizeT)(out - dest);
+  *srcLen = (SizeT)(in - src);
+  return res;
+}
+
 extern "C" SRes LzmaDec_DecodeToBuf(CLzmaDec *p, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
                                     ELzmaFinishMode finishMode, ELzmaStatus *status)
 {
-  /* reference LzmaDec.c:840-878: decode into the ring dictionary slice by slice, copy each slice out */
-  SizeT outSize = *destLen, inSize = *srcLen;
-  *srcLen = *destLen = 0;
-  for (;;)
-  {
-    SizeT inCur = inSize, outCur, dicPos;
-    ELzmaFinishMode mode;
-    if (p->dicPos == p->dicBufSize) p->dicPos = 0;
-    dicPos = p->dicPos;
-    if (outSize > p->dicBufSize - dicPos) { outCur = p->dicBufSize; mode = LZMA_FINISH_ANY; }
-    else { outCur = dicPos + outSize; mode = finishMode; }
-    SRes res = LzmaDec_DecodeToDic(p, outCur, src, &inCur, mode, status);
-    src += inCur; inSize -= inCur; *srcLen += inCur;
-    outCur = p->dicPos - dicPos;
-    memcpy(dest, p->dic + dicPos, outCur);
-    dest += outCur; outSize -= outCur; *destLen += outCur;
-    if (res != 0) return res;
-    if (outCur == 0 || outSize == 0) return SZ_OK;
-  }
+  return decode_to_buf(p, dest, destLen, src, srcLen, finishMode, status,
+                       [p](SizeT limit, const Byte *in, SizeT *inLen, ELzmaFinishMode mode, ELzmaStatus *st)
+                       { return LzmaDec_DecodeToDic(p, limit, in, inLen, mode, st); });
 }
 
 /* ------------------------------------------------------------------ LZMA2 state interface ----- */
@@ -361,24 +374,7 @@ extern "C" SRes Lzma2Dec_DecodeToDic(CLzma2Dec *p, SizeT dicLimit, const Byte *s
 extern "C" SRes Lzma2Dec_DecodeToBuf(CLzma2Dec *p, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen,
                                      ELzmaFinishMode finishMode, ELzmaStatus *status)
 {
-  /* reference Lzma2Dec.c:291-328 */
-  SizeT outSize = *destLen, inSize = *srcLen;
-  CLzmaDec *d = &p->decoder;
-  *srcLen = *destLen = 0;
-  for (;;)
-  {
-    SizeT inCur = inSize, outCur, dicPos;
-    ELzmaFinishMode mode;
-    if (d->dicPos == d->dicBufSize) d->dicPos = 0;
-    dicPos = d->dicPos;
-    if (outSize > d->dicBufSize - dicPos) { outCur = d->dicBufSize; mode = LZMA_FINISH_ANY; }
-    else { outCur = dicPos + outSize; mode = finishMode; }
-    SRes res = Lzma2Dec_DecodeToDic(p, outCur, src, &inCur, mode, status);
-    src += inCur; inSize -= inCur; *srcLen += inCur;
-    outCur = d->dicPos - dicPos;
-    memcpy(dest, d->dic + dicPos, outCur);
-    dest += outCur; outSize -= outCur; *destLen += outCur;
-    if (res != 0) return res;
-    if (outCur == 0 || outSize == 0) return SZ_OK;
-  }
+  return decode_to_buf(&p->decoder, dest, destLen, src, srcLen, finishMode, status,
+                       [p](SizeT limit, const Byte *in, SizeT *inLen, ELzmaFinishMode mode, ELzmaStatus *st)
+                       { return Lzma2Dec_DecodeToDic(p, limit, in, inLen, mode, st); });
 }

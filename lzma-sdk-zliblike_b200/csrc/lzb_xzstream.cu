@@ -275,26 +275,29 @@ static SRes stage_attach(IStateCoder *sc, UInt64 id, ISzAlloc *alloc)
 }
 
 /* ------------------------------------------------------------------ LZMA2 stage ----------------- */
+static CLzma2Dec *l2_of(void *stage) { return static_cast<CLzma2Dec *>(stage); }
+
 static void l2_free(void *pp, ISzAlloc *alloc)
 {
-  Lzma2Dec_Free((CLzma2Dec *)pp, alloc);
-  alloc->Free(alloc, pp);
+  CLzma2Dec *d = l2_of(pp);
+  Lzma2Dec_Free(d, alloc);                               /* device state, control block, dictionary */
+  alloc->Free(alloc, d);
 }
 
+/* LZMA2 as an xz filter has one property byte: the dictionary size code (xz format 5.3.1) */
 static SRes l2_set_props(void *pp, const Byte *props, size_t propSize, ISzAlloc *alloc)
 {
-  if (propSize != 1) return SZ_ERROR_UNSUPPORTED;
-  return Lzma2Dec_Allocate((CLzma2Dec *)pp, props[0], alloc);
+  return propSize == 1 ? Lzma2Dec_Allocate(l2_of(pp), props[0], alloc) : SZ_ERROR_UNSUPPORTED;
 }
 
-static void l2_init(void *pp) { Lzma2Dec_Init((CLzma2Dec *)pp); }
+static void l2_init(void *pp) { Lzma2Dec_Init(l2_of(pp)); }
 
 static SRes l2_code(void *pp, Byte *dest, SizeT *destLen, const Byte *src, SizeT *srcLen, int srcWasFinished,
                     ECoderFinishMode finishMode, int *wasFinished)
 {
   ELzmaStatus st;
   (void)srcWasFinished;
-  const SRes r = Lzma2Dec_DecodeToBuf((CLzma2Dec *)pp, dest, destLen, src, srcLen, (ELzmaFinishMode)finishMode, &st);
+  const SRes r = Lzma2Dec_DecodeToBuf(l2_of(pp), dest, destLen, src, srcLen, (ELzmaFinishMode)finishMode, &st);
   *wasFinished = st == LZMA_STATUS_FINISHED_WITH_MARK;
   return r;
 }
@@ -312,19 +315,16 @@ static SRes l2_attach(IStateCoder *sc, ISzAlloc *alloc)
 /* ------------------------------------------------------------------ filter chain ---------------- */
 extern "C" void MixCoder_Construct(CMixCoder *p, ISzAlloc *alloc)
 {
+  memset(p, 0, sizeof *p);                               /* no stages, no hand-over buffers yet */
   p->alloc = alloc;
-  p->buf = 0;
-  p->numCoders = 0;
-  for (int i = 0; i < MIXCODER_NUM_FILTERS_MAX; i++) p->coders[i].p = NULL;
 }
 
 extern "C" void MixCoder_Free(CMixCoder *p)
 {
-  for (int i = 0; i < p->numCoders; i++)
+  for (IStateCoder *st = p->coders, *end = p->coders + p->numCoders; st != end; st++)
   {
-    IStateCoder *sc = &p->coders[i];
-    if (p->alloc && sc->p) sc->Free(sc->p, p->alloc);
-    sc->p = NULL;
+    if (p->alloc && st->p) st->Free(st->p, p->alloc);
+    st->p = NULL;
   }
   p->numCoders = 0;
   if (p->buf) { p->alloc->Free(p->alloc, p->buf); p->buf = 0; }
@@ -338,11 +338,11 @@ extern "C" void MixCoder_Init(CMixCoder *p)
 
 extern "C" SRes MixCoder_SetFromMethod(CMixCoder *p, int coderIndex, UInt64 methodId)
 {
-  IStateCoder *sc = &p->coders[coderIndex];
+  IStateCoder *const slot = p->coders + coderIndex;
   p->ids[coderIndex] = methodId;
-  if (methodId == XZ_ID_LZMA2) return l2_attach(sc, p->alloc);
+  if (methodId == XZ_ID_LZMA2) return l2_attach(slot, p->alloc);
   if (coderIndex == 0) return SZ_ERROR_UNSUPPORTED;        /* a chain starts with a real decoder */
-  return stage_attach(sc, methodId, p->alloc);
+  return stage_attach(slot, methodId, p->alloc);
 }
 
 /* The chain of a block (xz format 3.1.2: filters are listed in the order the ENCODER applied them; the decoder runs
@@ -481,11 +481,9 @@ extern "C" SRes XzDec_Init(CMixCoder *p, const CXzBlock *block)
 extern "C" SRes XzUnpacker_Create(CXzUnpacker *p, ISzAlloc *alloc)
 {
   MixCoder_Construct(&p->decoder, alloc);
-  p->state = XZ_STATE_STREAM_HEADER;
+  p->state = XZ_STATE_STREAM_HEADER;                       /* at the first byte of the first stream's magic */
   p->pos = 0;
-  p->numStreams = 0;
-  p->numBlocks = 0;
-  p->padSize = 0;
+  p->numStreams = p->numBlocks = p->padSize = 0;
   return SZ_OK;
 }
 

@@ -310,7 +310,7 @@ class Job:
             self.local = wu                     # finish = the walker's "unit" mode: the last chunk's termination is validated
             self.walker = dict(api="Lzma2_IndexUnits", units=int(ix["n"]), ms=dt * 1e3, has_eos=bool(ix["has_eos"]))
 
-    def run(self, steps, warmup, e2e=True, verify_frac=0.01):
+    def run(self, steps, warmup, e2e=True, verify_frac=0.01, gather=False):
         import torch
         import lzb200
         R = lzb200.records
@@ -384,6 +384,7 @@ class Job:
         vres = d_results.cpu().numpy().view(R.RESULT_DTYPE)
         verified = reduce_all(ok and bool((vres["res"] == 0).all()))
         del d_vunits
+        gather_d = self.gather_on_rank0(d_out, verify_frac) if (gather and dist and not self.replicate) else None
 
         # e2e: host arenas through the C-ABI, copies inside the timed region
         e2e_d = None
@@ -421,7 +422,45 @@ class Job:
         kms = float(np.mean(kernel_ms))
         return dict(value=value, ms_per_step=ms_per_step, kernel_ms=kms, clocks=clocks, verified=verified, e2e=e2e_d,
                     alg_bytes=int(units["src_len"].astype(np.uint64).sum() + units["dst_cap"].astype(np.uint64).sum()),
-                    units_this_rank=n, my_ms_per_step=my_ms / steps)
+                    units_this_rank=n, my_ms_per_step=my_ms / steps, gather=gather_d)
+
+    def gather_on_rank0(self, d_out, verify_frac):
+        """SURVEY 8e's optional step: the ranks' output slabs are contiguous ranges of the decoded stream, so rank 0
+        receives each one at its offset (NCCL point-to-point over NVLink) and ends up with the whole stream on one GPU."""
+        import torch
+        env = self.env
+        dev, dist, world, rank = env["dev"], env["dist"], env["world"], env["rank"]
+        import lzb200
+        bounds = lzb200.sharding.slab_bounds(dist, self.dst_lo, self.dst_hi, dev)
+        total = bounds[-1][1]
+        d_full = torch.empty(total, dtype=torch.uint8, device=dev) if rank == 0 else None
+        slab = d_out[: self.dst_hi - self.dst_lo]
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            lzb200.sharding.gather_slabs(dist, slab, bounds, d_full, root=0)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            best = float(tt.item()) if best is None else min(best, float(tt.item()))
+        if rank != 0:
+            return None
+        gu, ok, checked = self.g["units"], True, 0
+        stride = max(1, int(1.0 / max(verify_frac, 1e-6)))
+        for j in range(0, len(gu), stride):
+            o, ln = int(gu["dst_off"][j]), int(gu["dst_cap"][j])
+            ok = ok and zlib.crc32(d_full[o:o + ln].cpu().numpy().tobytes()) == int(self.w["crc32"][self.g["idx"][j]])
+            checked += 1
+        return dict(to="rank 0's GPU", api="torch.distributed batch_isend_irecv (NCCL point-to-point over NVLink)", bytes=total,
+                    bytes_received=total - (bounds[0][1] - bounds[0][0]), ms=best, GBps=total / (best * 1e-3) / 1e9,
+                    verified=bool(ok), host_crc32_checked_units=checked,
+                    note="outside the timed region; best of 3; the device-to-device copy of rank 0's own slab is included")
 
 
 def roofline_of(name: str, r: dict, geometry_note: str):
@@ -449,12 +488,16 @@ def roofline_of(name: str, r: dict, geometry_note: str):
 
 
 def geometry_note(n_units_rank: int, sms: int) -> str:
+    """What lzb_plan_few_units picks at the default properties (36 resident units per SM): DESIGN.md 2 / 4a."""
     per_sm = n_units_rank / max(sms, 1)
     if n_units_rank <= sms * 16:
-        return (f"{n_units_rank} units on this GPU = {per_sm:.1f} per SM: one unit per warp (lzb_decode_units_kernel<1,32,*>); the limiter is "
-                "single-unit latency, not a collective")
-    return (f"{n_units_rank} units on this GPU = {per_sm:.1f} per SM over 36 resident (two per warp, lzb_decode_units_kernel<1,16,*>): "
-            "issue-slot bound")
+        return (f"{n_units_rank} units on this GPU = {per_sm:.1f} per SM: one unit per warp in one wave, look-ahead form of the decoder "
+                "(lzb_decode_units_kernel<1,32,*,1>); the limiter is the issue rate of a unit's own warp, not a collective")
+    if n_units_rank <= sms * 29:
+        return (f"{n_units_rank} units on this GPU = {per_sm:.1f} per SM: one unit per warp, 16 persistent warps per SM taking units from "
+                "the ticket, look-ahead form (lzb_decode_units_kernel<1,32,*,1>)")
+    return (f"{n_units_rank} units on this GPU = {per_sm:.1f} per SM over 36 resident (two per warp, lean form, "
+            "lzb_decode_units_kernel<1,16,*,0>): issue-slot bound")
 
 
 # ------------------------------------------------------------------------------------ extras: configs 5 and 1
@@ -579,6 +622,8 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny corpus, for smoke-testing the harness")
     ap.add_argument("--weak", action="store_true", help="replicate the job on every rank instead of sharding it")
     ap.add_argument("--extras", default="auto", help="auto | all | none | comma list of weak_lzma64k,xz4m,7z,lzma_stream")
+    ap.add_argument("--gather", action="store_true", help="N > 1: after the timed steps, collect every rank's output slab on rank 0's GPU "
+                                                          "over NVLink (NCCL send/recv) and report the time as an extra key")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
@@ -653,7 +698,7 @@ def main():
     job = Job(a.workload, n_units, a, env, replicate=weak)
     job.stage()
     log(f"{a.workload}: staged {job.count} of {n_units} units on rank 0 in {time.time() - t_start:.1f} s")
-    r = job.run(a.steps, a.warmup, e2e=not a.no_e2e)
+    r = job.run(a.steps, a.warmup, e2e=not a.no_e2e, gather=a.gather)
     log(f"{a.workload}: value {r['value']:.3f} GB/s, e2e {r['e2e']['value'] if r['e2e'] else None}")
     note = geometry_note(r["units_this_rank"], ctx.sms or 148)
     roofline = roofline_of(a.workload, r, note)
@@ -753,6 +798,8 @@ def main():
                     ratio=dict(packed_over_unpacked=ratio))
         if container:
             line["container_e2e"] = container
+        if r.get("gather"):
+            line["gather"] = r["gather"]
         if configs:
             line["configs"] = configs
         print(json.dumps(line))

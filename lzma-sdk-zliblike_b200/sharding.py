@@ -57,3 +57,30 @@ def reduce_job(dist, seconds: float, worst_res: int, out_bytes: int, device=None
     s = torch.tensor([float(out_bytes)], dtype=torch.float64, device=device)
     dist.all_reduce(s, op=dist.ReduceOp.SUM)
     return float(t[0]), int(t[1]), int(s[0])
+
+
+def slab_bounds(dist, dst_lo: int, dst_hi: int, device=None):
+    """[(dst_lo, dst_hi)] of every rank, in rank order (the slabs tile the output arena)."""
+    import torch
+    mine = torch.tensor([dst_lo, dst_hi], dtype=torch.int64, device=device)
+    every = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(every, mine)
+    return [tuple(int(v) for v in b.tolist()) for b in every]
+
+
+def gather_slabs(dist, slab, bounds, full=None, root: int = 0):
+    """SURVEY 8e's optional step: collect every rank's output slab at its offset of `full` on `root`.
+    Point-to-point (NCCL over NVLink on GPUs, gloo in the CPU test): the slabs are ragged and only one rank wants them,
+    so this is one receive per peer posted together, not a collective.  `slab`: this rank's bytes (uint8 tensor of
+    exactly bounds[rank] length); `full`: on `root`, a uint8 tensor of bounds[-1][1] bytes."""
+    rank = dist.get_rank()
+    if rank == root:
+        lo, hi = bounds[root]
+        full[lo:hi].copy_(slab)
+        ops = [dist.P2POp(dist.irecv, full[lo:hi], src) for src, (lo, hi) in enumerate(bounds) if src != root and hi > lo]
+    else:
+        ops = [dist.P2POp(dist.isend, slab, root)] if slab.numel() else []
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return full

@@ -1,4 +1,5 @@
-"""N>1 path on CPU: the static unit partition + the job-level reductions, world_size 2 and 3 over gloo.
+"""N>1 path on CPU: the static unit partition + the job-level reductions + the optional gather of the output slabs,
+world_size 2 and 3 over gloo.
 (No decode here -- the units are decoded per rank by the same single-GPU path the gpu tests cover; what
 multi-GPU adds is only the partition and the max/sum bookkeeping.)"""
 import os
@@ -66,7 +67,18 @@ def _worker(rank, world, port, q):
     import torch
     cover = [None] * world
     dist.all_gather_object(cover, (first, len(loc), src_lo, src_hi, dst_lo, dst_hi))
-    q.put((rank, t, res, total, cover, int(loc["src_off"].min()) if len(loc) else 0))
+    # the optional gather of 8e: every rank fills its slab with a function of the GLOBAL byte offset, rank 0 collects
+    # (slab sizes scaled down 1024x: the table describes 2.6 GB of output)
+    dst_lo, dst_hi = dst_lo >> 10, dst_hi >> 10
+    bounds = lzb200.sharding.slab_bounds(dist, dst_lo, dst_hi)
+    slab = torch.from_numpy(((np.arange(dst_lo, dst_hi, dtype=np.uint64) * 2654435761 >> 7) & 0xFF).astype(np.uint8))
+    full = torch.zeros(bounds[-1][1], dtype=torch.uint8) if rank == 0 else None
+    lzb200.sharding.gather_slabs(dist, slab, bounds, full, root=0)
+    gathered_ok = None
+    if rank == 0:
+        want = ((np.arange(0, bounds[-1][1], dtype=np.uint64) * 2654435761 >> 7) & 0xFF).astype(np.uint8)
+        gathered_ok = bool(np.array_equal(full.numpy(), want))
+    q.put((rank, t, res, total, cover, int(loc["src_off"].min()) if len(loc) else 0, gathered_ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -92,7 +104,8 @@ def _run(world):
         assert p.exitcode == 0
     u = _table(5000, 42)
     total = int(u["dst_cap"].astype(np.uint64).sum())
-    for rank, t, res, tot, cover, local_min in got:
+    for rank, t, res, tot, cover, local_min, gathered_ok in got:
+        assert gathered_ok is (True if rank == 0 else None)
         assert abs(t - (0.5 + 0.25 * (world - 1))) < 1e-9       # max over ranks
         assert res == 1 and tot == total and local_min == 0
         cover = sorted(cover)

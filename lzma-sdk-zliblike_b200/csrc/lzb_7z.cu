@@ -350,7 +350,7 @@ SRes classify_folder(const Folder &f, LzbSzFolder &o)
   o.method = m.method == kMethodCopy ? 0u : (m.method == kMethodLzma ? 1u : 2u);
   o.props_size = (uint8_t)(m.props.size() > 255 ? 255 : m.props.size());
   memset(o.props, 0, sizeof o.props);
-  memcpy(o.props, m.props.data(), m.props.size() < sizeof o.props ? m.props.size() : sizeof o.props);
+  if (!m.props.empty()) memcpy(o.props, m.props.data(), m.props.size() < sizeof o.props ? m.props.size() : sizeof o.props);
   o.filter = LZB_FILTER_NONE;
   if (n == 1)
     return (f.pack_streams.size() == 1 && f.pack_streams[0] == 0 && f.binds.empty()) ? SZ_OK : SZ_ERROR_UNSUPPORTED;
@@ -750,7 +750,7 @@ static SRes read_header(Cursor &c, LzbSzArchive &a, UInt64 start_after_header)
         SubCoder &sc = b.sub[ci];
         sc.method = cd.method == kMethodCopy ? 0u : (cd.method == kMethodLzma ? 1u : 2u);
         sc.props_size = (uint8_t)(cd.props.size() > 255 ? 255 : cd.props.size());
-        memcpy(sc.props, cd.props.data(), cd.props.size() < sizeof sc.props ? cd.props.size() : sizeof sc.props);
+        if (!cd.props.empty()) memcpy(sc.props, cd.props.data(), cd.props.size() < sizeof sc.props ? cd.props.size() : sizeof sc.props);
         sc.pack_off = off[stream_of[ci]]; sc.pack_size = db.pack_sizes[pack_index + (size_t)stream_of[ci]];
         sc.unpack_size = f.unpack_sizes[(size_t)ci];
       }

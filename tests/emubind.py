@@ -15,7 +15,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(ROOT, "lzma-sdk-zliblike_b200", "csrc")
-SO = os.path.join(HERE, "emu", "_build", "libemu.so")
+# LZB_EMU_SANITIZE=1: the same source with AddressSanitizer + UBSan (run python with the sanitizer runtimes preloaded,
+# tools/emu_sanitize.sh) -- compute-sanitizer's stand-in for the device code's index arithmetic
+SANITIZE = os.environ.get("LZB_EMU_SANITIZE") == "1"
+SO = os.path.join(HERE, "emu", "_build", "libemu_san.so" if SANITIZE else "libemu.so")
 SRC = os.path.join(HERE, "emu", "emu_core.cpp")
 
 _lib = None
@@ -35,7 +38,8 @@ def lib():
     if _lib is None:
         if _stale():
             os.makedirs(os.path.dirname(SO), exist_ok=True)
-            subprocess.check_call(["g++", "-O1", "-g", "-shared", "-fPIC", "-std=c++17", "-Wno-unknown-pragmas",
+            san = ["-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer"] if SANITIZE else []
+            subprocess.check_call(["g++", "-O1", "-g", "-shared", "-fPIC", "-std=c++17", "-Wno-unknown-pragmas", *san,
                                    "-I", CSRC, SRC, "-o", SO])
         _lib = C.CDLL(SO)
         _lib.emu_decode_units.restype = C.c_int
@@ -69,14 +73,19 @@ class Emu:
         import lzb200
         R = lzb200.records
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
-        pad = np.zeros(len(packed) + 64, np.uint8)
         skew = 13                                           # deliberately unaligned unit start
+        # under the sanitizers the arenas end where the contract says they may: the packed arena at the end of the last
+        # 32-bit word that holds a byte of the unit, the output arena at dst_off + dst_cap (redzones right behind)
+        pad = np.zeros((skew + len(packed) + 3) // 4 * 4 if SANITIZE else len(packed) + 64, np.uint8)
         pad[skew:skew + len(packed)] = packed
         u = R.make_units(1)
         u["src_off"], u["src_len"], u["dst_off"], u["dst_cap"] = skew, len(packed), 3, cap
         fill(u, R)
-        out = np.zeros(max(cap, 1) + 64, np.uint8)
+        out = np.zeros(3 + cap if SANITIZE else max(cap, 1) + 64, np.uint8)
+        out[:3] = 0xA5
         r = decode_units(pad, out, u)[0]
+        # bytes of the arena in front of and behind the unit's slice belong to other units
+        assert (out[:3] == 0xA5).all() and not out[3 + cap:].any(), "the unit wrote outside [dst_off, dst_off + dst_cap)"
         # LZB_ST_INHERIT (-1): the unit never assigned *status; a fresh call starts from NOT_SPECIFIED
         return dict(res=int(r["res"]), status=max(int(r["status"]), 0), dest_len=int(r["dst_done"]),
                     src_len=int(r["src_used"]), out=out[3:3 + cap], check=int(r["check"]))
@@ -106,12 +115,13 @@ class Emu:
     def _post(self, data, **kw):
         import lzb200
         R = lzb200.records
-        buf = np.concatenate((np.zeros(5, np.uint8), np.ascontiguousarray(data, dtype=np.uint8), np.zeros(8, np.uint8)))
+        buf = np.concatenate((np.full(5, 0xA5, np.uint8), np.ascontiguousarray(data, dtype=np.uint8), np.zeros(0 if SANITIZE else 8, np.uint8)))
         u = R.make_units(1)
         u["dst_off"], u["dst_cap"] = 5, len(data)
         for k, v in kw.items():
             u[k] = v
         r = post_units(buf, u)[0]
+        assert (buf[:5] == 0xA5).all() and not buf[5 + len(data):].any(), "the pass wrote outside the unit's bytes"
         return buf[5:5 + len(data)], r
 
     def x86_convert(self, data, ip=0, state=0, encoding=0):

@@ -167,7 +167,7 @@ lzb_decode_units_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict_
         d.finish_unit(r);
         /* (inlined on purpose: out of line, with the unit and result records forced into local memory, the dense
          * instantiation ran 2 % slower -- profiles/r02_kernel_log.md) */
-        if (!(u.flags & LZB_UNIT_STATEFUL)) post_process<G>(u, r, dst, region, reinterpret_cast<uint8_t *>(matched), kSharedModel ? region_bytes : kPostSmemBytes);
+        if (!(u.flags & LZB_UNIT_STATEFUL)) post_process<G, false, kAhead>(u, r, dst, region, reinterpret_cast<uint8_t *>(matched), kSharedModel ? region_bytes : kPostSmemBytes);
         if (Grp::lane() == 0) results[ui] = r;
         Grp::sync();
         if (kFlow && flow.done) flow_done<G>(flow, ui, n_units);

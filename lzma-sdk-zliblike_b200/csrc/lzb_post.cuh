@@ -5,10 +5,9 @@
  * table (kPostSmemBytes of the shared-memory region) and the Delta filter's per-lane column sums
  * (kPostScratchBytes of the matched-literal slab slice in HBM/L2).
  *
- *  x86 BCJ  (Bra86.c:11-85)   sequential state (3-bit history of recent E8/E9 candidates) resets after
- *           four bytes without an opcode candidate, and a conversion never reaches across such a gap;
- *           every lane therefore starts at the first such "safe point" at or after its nominal
- *           boundary and runs the scalar converter up to the next lane's start.
+ *  x86 BCJ  (Bra86.c:11-85)   the opcode candidates (E8/E9) have to be decided in order (3-bit history), but they are
+ *           sparse: the group finds them with coalesced 16-byte loads per lane, a tile of G x 16 bytes at a time, and
+ *           walks the marked positions in order (ballot + broadcast), every lane running the same decision.
  *  Delta    (Delta.c:43-62)   out[i] = in[i] + out[i-d] is a prefix sum per residue class mod d:
  *           per-lane column sums -> exclusive scan across lanes -> second sweep.
  *  CRC      (7zCrc.c, 7zCrcOpt.c, XzCrc64.c)  slicing tables in the group's scratch (four bytes per dependent step
@@ -81,8 +80,11 @@ LZB_FN uint32_t x86_convert_range(uint8_t *data, uint32_t from, uint32_t to, uin
   return pos;
 }
 
-/* Whole-buffer x86_Convert.  Returns the processed byte count; *state in/out as in the reference. */
-template <uint32_t G> LZB_FN uint32_t x86_convert_group(uint8_t *data, uint32_t size, uint32_t ip, bool encoding, uint32_t &state)
+/* Whole-buffer x86_Convert, one contiguous segment per lane (round 1).  Still what the LEAN decode kernels carry: their
+ * hot loop's register allocation depends on the cold code inlined next to it, and with the tile scan below in its place
+ * the dense launches ran 3 % (inlined) to 8 % (out of line) slower on workloads that have no filter at all
+ * (profiles/r02_z_x86_tiles.md); their SASS is byte-identical to the library of the sessions before. */
+template <uint32_t G> LZB_FN uint32_t x86_convert_lanes(uint8_t *data, uint32_t size, uint32_t ip, bool encoding, uint32_t &state)
 {
   typedef Group<G> Grp;
   if (size < 5) return 0;                               /* Bra86.c:15-16 (state untouched) */
@@ -127,6 +129,151 @@ template <uint32_t G> LZB_FN uint32_t x86_convert_group(uint8_t *data, uint32_t 
   pos = Grp::bcast(pos, top);
   last = Grp::bcast(last, top);
   hist = Grp::bcast(hist, top);
+  const uint32_t gap = pos - last;
+  state = gap > 3 ? 0 : ((hist << (gap - 1)) & 7);      /* Bra86.c:82-83 */
+  return pos;
+}
+
+/* One opcode candidate at `pos` (Bra86.c:26-80): updates the 3-bit neighbour history `hist` and the previous candidate
+ * position `last`, converts the operand when the rules allow it, and returns where the scan goes on (pos + 1, or pos + 5
+ * behind a conversion).  Everything it READS is original data: a conversion rewrites pos+1 .. pos+4 and resumes at
+ * pos+5, and no later candidate looks further back than its own pos+1.  `store`: this lane writes the result (the
+ * lanes of a group run the decision redundantly on the same bytes). */
+LZB_FN uint32_t x86_candidate(uint8_t *data, uint32_t pos, uint32_t ip5, bool encoding, uint32_t &hist, uint32_t &last, bool store)
+{
+  /* kMaskToAllowedStatus / kMaskToBitNumber (Bra86.c:8-9) packed into immediates */
+  const uint32_t allow = 0x17;          /* bit h set  <=> history h allows a conversion: {1,1,1,0,1,0,0,0} */
+  const uint32_t topbit = 0x6DB488u;    /* 3 bits per h: {0,1,2,2,3,3,3,3} */
+  const uint32_t gap = pos - last;
+  last = pos;
+  if (gap > 3) hist = 0;
+  else
+  {
+    hist = (hist << (gap - 1)) & 7;
+    if (hist != 0)
+    {
+      const uint8_t b = data[pos + 4 - ((topbit >> (3 * hist)) & 7)];
+      if (!((allow >> hist) & 1) || is_fill(b)) { hist = ((hist << 1) & 7) | 1; return pos + 1; }
+    }
+  }
+  if (!is_fill(data[pos + 4])) { hist = ((hist << 1) & 7) | 1; return pos + 1; }
+  uint32_t v = ((uint32_t)data[pos + 4] << 24) | ((uint32_t)data[pos + 3] << 16) | ((uint32_t)data[pos + 2] << 8) | data[pos + 1];
+  const uint32_t here = ip5 + pos;
+  uint32_t out;
+  for (;;)
+  {
+    out = encoding ? here + v : v - here;
+    if (hist == 0) break;
+    const uint32_t sh = ((topbit >> (3 * hist)) & 7) * 8;
+    if (!is_fill((uint8_t)(out >> (24 - sh)))) break;
+    v = out ^ ((1u << (32 - sh)) - 1);
+  }
+  if (store)
+  {
+    data[pos + 4] = (uint8_t)(0u - ((out >> 24) & 1));
+    data[pos + 3] = (uint8_t)(out >> 16);
+    data[pos + 2] = (uint8_t)(out >> 8);
+    data[pos + 1] = (uint8_t)out;
+  }
+  return pos + 5;
+}
+
+/* the 16 bytes at data + at (a 16-byte-aligned ADDRESS) as one vector load when all of them are the unit's, byte by byte
+ * at the two ends of the buffer; bytes outside [0, size) read as 0 */
+LZB_FN void x86_load16(const uint8_t *data, int64_t at, uint32_t size, uint32_t w[4])
+{
+  if (at >= 0 && at + 16 <= (int64_t)size)
+  {
+#ifdef LZB_EMU
+    memcpy(w, data + at, 16);
+#else
+    const uint4 v = *reinterpret_cast<const uint4 *>(data + at);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+#endif
+    return;
+  }
+  w[0] = w[1] = w[2] = w[3] = 0;
+  if (at + 16 <= 0 || at >= (int64_t)size) return;
+#pragma unroll
+  for (int k = 0; k < 4; k++)                            /* w[] stays in registers: static index, rolled inner loop */
+  {
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int j = 0; j < 4; j++)
+    {
+      const int64_t q = at + 4 * k + j;
+      if (q >= 0 && q < (int64_t)size) acc |= (uint32_t)data[q] << (8 * j);
+    }
+    w[k] = acc;
+  }
+}
+
+/* bit j set <=> byte j of the 16 is an opcode candidate (E8 / E9) */
+LZB_FN uint32_t x86_opcode_mask16(const uint32_t w[4])
+{
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 16; j++) m |= (((w[j >> 2] >> (8 * (j & 3))) & 0xFEu) == 0xE8u ? 1u : 0u) << j;
+  return m;
+}
+
+/* Whole-buffer x86_Convert by one group.  Returns the processed byte count; *state in/out as in the reference.
+ *
+ * The candidates have to be taken in order (each decision depends on the history the earlier ones left), but they
+ * are sparse, and finding them is what the bytes cost: the group sweeps the buffer in tiles of G x 16 bytes, every
+ * lane loads one aligned 16-byte vector (a coalesced tile, the next one already in flight) and marks its opcode
+ * bytes; the group then walks the marked positions in ascending order -- ballot for the first lane that has one at
+ * or behind the scan position, broadcast of its lowest bit -- and every lane runs the (uniform) decision of
+ * `x86_candidate` on it, lane 0 storing.  Marks are taken from original bytes and positions a conversion jumps over
+ * are simply behind the scan position, so nothing needs to be re-read.  (Before: one contiguous segment per lane
+ * scanned byte by byte from "safe points" -- G uncoalesced byte streams, 52 ms for a 4 MiB block, 3.6 % of the
+ * `xz4m` launch: profiles/r02_y_post_share.md.) */
+#ifdef LZB_EMU
+#define LZB_COLD_FN inline
+#else
+#define LZB_COLD_FN __device__ __noinline__
+#endif
+template <uint32_t G> LZB_COLD_FN uint32_t x86_convert_tiles(uint8_t *data, uint32_t size, uint32_t ip, bool encoding, uint32_t &state)
+{
+  typedef Group<G> Grp;
+  if (size < 5) return 0;                               /* Bra86.c:15-16 (state untouched) */
+  const uint32_t stop = size - 4;                       /* candidates live in [0, stop) */
+  const uint32_t lane = Grp::lane();
+  Grp::sync();                                          /* the decode's stores of the other lanes are visible */
+  uint32_t hist = state & 7;
+  uint32_t last = 0xFFFFFFFFu;                          /* prevPosT = -1 (Bra86.c:18) */
+  uint32_t pos = 0;
+  const uint32_t ip5 = ip + 5;
+  const int64_t tile = (int64_t)G * 16;
+  int64_t at = -(int64_t)((uintptr_t)data & 15) + (int64_t)lane * 16;    /* this lane's 16 bytes of the current tile */
+  uint32_t cur[4], nxt[4];
+  x86_load16(data, at, size, cur);
+  for (int64_t tb = at - (int64_t)lane * 16; tb < (int64_t)stop; tb += tile, at += tile)
+  {
+    x86_load16(data, at + tile, size, nxt);
+    uint32_t m = x86_opcode_mask16(cur);
+    if (at + 16 > (int64_t)stop) m = at >= (int64_t)stop ? 0u : m & ((1u << (uint32_t)((int64_t)stop - at)) - 1u);
+    for (;;)
+    {
+      const int64_t rel = (int64_t)pos - at;             /* marks below the scan position are behind us */
+      const uint32_t mm = rel <= 0 ? m : (rel >= 16 ? 0u : m & (0xFFFFu << (uint32_t)rel));
+      const uint32_t have = Grp::ballot(mm != 0);
+      if (have == 0) break;
+#ifdef LZB_EMU
+      const uint32_t owner = (uint32_t)__builtin_ctz(have);
+      const uint32_t mine = (uint32_t)at + (uint32_t)__builtin_ctz(mm | 0x10000u);
+#else
+      const uint32_t owner = (uint32_t)__ffs((int)have) - 1u;
+      const uint32_t mine = (uint32_t)at + (uint32_t)__ffs((int)(mm | 0x10000u)) - 1u;
+#endif
+      const uint32_t c = Grp::bcast(mine, owner);
+      pos = x86_candidate(data, c, ip5, encoding, hist, last, lane == 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) cur[j] = nxt[j];
+  }
+  Grp::sync();                                          /* lane 0's stores are visible to the check that follows */
+  if (pos < stop) pos = stop;
   const uint32_t gap = pos - last;
   state = gap > 3 ? 0 : ((hist << (gap - 1)) & 7);      /* Bra86.c:82-83 */
   return pos;
@@ -424,7 +571,9 @@ template <uint32_t G> LZB_FN void delta_encode_group(uint8_t *data, uint32_t n, 
  *                 column sums (up to 256 x G bytes; Delta blocks are rare, L2 latency is acceptable). */
 /* kRisc: also the stateless RISC converters (only the stand-alone / second-pass kernel carries them, the
  * fused decode kernel stays lean: BCJ x86 and Delta are what the reference's own writers emit). */
-template <uint32_t G, bool kRisc = false>
+/* kTiles: x86 BCJ as the tile scan (look-ahead decode kernels, the stand-alone / second-pass kernel) or as per-lane
+ * segments (lean decode kernels, see x86_convert_lanes) -- same results, tests run both. */
+template <uint32_t G, bool kRisc = false, bool kTiles = true>
 LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t *scratch, uint8_t *big_scratch,
                          uint32_t scratch_bytes = kPostSmemBytes)
 {
@@ -435,7 +584,8 @@ LZB_FN void post_process(const LzbUnit &u, LzbResult &r, uint8_t *data, uint8_t 
     /* stand-alone x86_Convert calls pass the direction in flags bit 1 and the history in `expect`; a filter fused
      * behind a decode starts a block / folder with no history (`expect` is the stored digest there) */
     uint32_t st = (u.flags & LZB_UNIT_POST_REPORT) ? ((uint32_t)(u.expect >> 32) & 7) : 0u;
-    const uint32_t done = x86_convert_group<G>(data, n, u.filter_param, (u.flags & 2) != 0, st);
+    const uint32_t done = kTiles ? x86_convert_tiles<G>(data, n, u.filter_param, (u.flags & 2) != 0, st)
+                                 : x86_convert_lanes<G>(data, n, u.filter_param, (u.flags & 2) != 0, st);
     if (u.flags & 4) { r.src_used = done; r.status = (int32_t)st; }   /* stand-alone call: report them */
   }
   else if (u.filter == LZB_FILTER_DELTA)

@@ -14,6 +14,9 @@
 #include "lzb_post.cuh"
 
 /* filter / check only, like lzb_post_only_kernel */
+static int g_post_lanes = 0;          /* 1: the per-lane x86 converter of the lean decode kernels instead of the tile scan */
+extern "C" void emu_post_use_lanes(int on) { g_post_lanes = on; }
+
 extern "C" int emu_post_units(uint8_t *data, const LzbUnit *units, LzbResult *results, uint32_t n)
 {
   std::vector<uint8_t> scratch(lzb::kPostScratchBytes);
@@ -22,7 +25,8 @@ extern "C" int emu_post_units(uint8_t *data, const LzbUnit *units, LzbResult *re
     const LzbUnit &u = units[i];
     LzbResult r;
     r.res = LZB_SZ_OK; r.status = LZB_ST_NOT_SPECIFIED; r.src_used = 0; r.dst_done = u.dst_cap; r.check = 0;
-    lzb::post_process<1, true>(u, r, data + u.dst_off, scratch.data(), scratch.data(), lzb::kPostScratchBytes);
+    if (g_post_lanes) lzb::post_process<1, true, false>(u, r, data + u.dst_off, scratch.data(), scratch.data(), lzb::kPostScratchBytes);
+    else lzb::post_process<1, true, true>(u, r, data + u.dst_off, scratch.data(), scratch.data(), lzb::kPostScratchBytes);
     results[i] = r;
   }
   return 0;
@@ -56,7 +60,8 @@ static int decode_units(const uint8_t *packed, uint8_t *out, const LzbUnit *unit
       d.step();
     }
     d.finish_unit(r);
-    if (!stateful) lzb::post_process<1>(u, r, out + u.dst_off, (uint8_t *)probs.data(), (uint8_t *)matched.data(), ns * 2);
+    /* like the kernel: the lean form carries the per-lane x86 converter, the look-ahead form the tile scan */
+    if (!stateful) lzb::post_process<1, false, kAhead>(u, r, out + u.dst_off, (uint8_t *)probs.data(), (uint8_t *)matched.data(), ns * 2);
     results[i] = r;
   }
   return 0;

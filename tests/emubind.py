@@ -62,6 +62,7 @@ def decode_units(packed: np.ndarray, out: np.ndarray, units: np.ndarray) -> np.n
 def post_units(data: np.ndarray, units: np.ndarray) -> np.ndarray:
     import lzb200
     res = np.zeros(len(units), dtype=lzb200.records.RESULT_DTYPE)
+    lib().emu_post_use_lanes(0 if AHEAD else 1)        # lean form: per-lane x86 converter; look-ahead form: the tile scan
     lib().emu_post_units(data.ctypes.data, units.ctypes.data, res.ctypes.data, len(units))
     return res
 

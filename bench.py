@@ -318,7 +318,7 @@ class Job:
         dev, ctx, dist, world = env["dev"], env["ctx"], env["dist"], env["world"]
         units = self.local
         n = self.count
-        # measurement aid (profiles/r02_y_post_share.md): LZB_BENCH_POST=none|crc|x86 strips the fused post pass (or half of
+        # measurement aid (profiles/r02_z_x86_tiles.md): LZB_BENCH_POST=none|crc|x86 strips the fused post pass (or half of
         # it) from an xz4m unit table, so that the difference in kernel time is what it costs; such a line is not verified
         post_mode = os.environ.get("LZB_BENCH_POST", "all") if int(self.w["kind"]) == 2 else "all"
         if post_mode != "all":

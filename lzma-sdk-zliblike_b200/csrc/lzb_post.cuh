@@ -227,7 +227,7 @@ LZB_FN uint32_t x86_opcode_mask16(const uint32_t w[4])
  * `x86_candidate` on it, lane 0 storing.  Marks are taken from original bytes and positions a conversion jumps over
  * are simply behind the scan position, so nothing needs to be re-read.  (Before: one contiguous segment per lane
  * scanned byte by byte from "safe points" -- G uncoalesced byte streams, 52 ms for a 4 MiB block, 3.6 % of the
- * `xz4m` launch: profiles/r02_y_post_share.md.) */
+ * `xz4m` launch: profiles/r02_z_x86_tiles.md.) */
 #ifdef LZB_EMU
 #define LZB_COLD_FN inline
 #else

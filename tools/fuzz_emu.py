@@ -19,16 +19,52 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from tools.fuzz_gpu import shape  # noqa: E402
 
 
+def fuzz_x86(a, ref, emu, emubind):
+    """x86_Convert: both converters of lzb_post.cuh (per-lane segments = lean form, tile scan = look-ahead form) on buffers
+    full of opcode candidates and fill bytes, every carried state, both directions, unaligned starts"""
+    rng = np.random.default_rng(a.seed)
+    total = bad = 0
+    for it in range(a.rounds * 500):
+        n = int(rng.choice([5, 6, 7, 9, 15, 16, 17, 20, 31, 32, 33, 47, 48, 49, 64, 100, 257, 1000, 5000]))
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            d = rng.integers(0, 256, n, dtype=np.uint8)
+        elif kind == 1:
+            d = rng.choice(np.array([0xE8, 0xE9, 0x00, 0xFF, 0x12, 0x80], dtype=np.uint8), n, p=[.25, .15, .25, .2, .1, .05])
+        elif kind == 2:
+            d = rng.choice(np.array([0xE8, 0x00, 0xFF], dtype=np.uint8), n)
+        else:
+            d = rng.integers(0, 256, n, dtype=np.uint8)
+            for k in range(0, n - 5, int(rng.integers(5, 40))):
+                d[k] = 0xE8
+                d[k + 4] = 0 if rng.integers(0, 2) else 0xFF
+        ip, st, enc = int(rng.integers(0, 1 << 32)), int(rng.integers(0, 8)), int(rng.integers(0, 2))
+        w = ref.x86_convert(d, ip, st, enc)
+        for form in (0, 1):
+            emubind.AHEAD = form
+            g = emu.x86_convert(d, ip, st, enc)
+            total += 1
+            if not (np.array_equal(w[0], g[0]) and w[1] == g[1] and w[2] == g[2]):
+                bad += 1
+                print(f"MISMATCH x86 n {n} kind {kind} form {form} ip {ip} state {st} enc {enc}: ref {w[1:]} emu {g[1:]}", flush=True)
+    emubind.AHEAD = 0
+    print("FUZZ emu x86", "FAILED" if bad else "OK", total, "conversions", bad, "mismatches", "(sanitizers on)" if emubind.SANITIZE else "")
+    return 1 if bad else 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=20)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--x86", action="store_true", help="fuzz the x86 BCJ converters instead of the decoder")
     a = ap.parse_args()
     import emubind
     from oracle import refbind
     ref = refbind.ref()
     emu = emubind.Emu()
     emubind.lib()
+    if a.x86:
+        return fuzz_x86(a, ref, emu, emubind)
     rng = np.random.default_rng(a.seed)
     total = bad = 0
     for rd in range(a.rounds):

@@ -817,16 +817,20 @@ SRes combined_decode(LzbContext *c, OneCall &me)
 {
   Combiner &q = g_combiner;
   std::unique_lock<std::mutex> lk(q.mu);
-  q.waiting.push_back(&me);
+  try { q.waiting.push_back(&me); }
+  catch (...) { return SZ_ERROR_MEM; }
   while (!me.done && q.busy) me.cv.wait(lk);
   if (me.done) return me.call_res;                    /* a leader served this call */
   q.busy = true;                                      /* lead: everything that is waiting now, this call included */
   std::vector<OneCall *> batch;
   batch.swap(q.waiting);
   lk.unlock();
-  run_batch(c, batch);
+  SRes failed = SZ_OK;                                /* nobody of the batch may be left waiting, whatever happens */
+  try { run_batch(c, batch); }
+  catch (...) { failed = SZ_ERROR_MEM; }
   lk.lock();
   q.busy = false;
+  if (failed != SZ_OK) for (OneCall *o : batch) o->call_res = failed;
   for (OneCall *o : batch) if (o != &me) { o->done = true; o->cv.notify_one(); }
   if (!q.waiting.empty()) q.waiting.front()->cv.notify_one();      /* the next batch gets its leader */
   return me.call_res;

@@ -66,6 +66,24 @@ def test_branch_converters_and_delta_encode(ora, emu):
             cases.check_bra_case(impl, c, blobs)
 
 
+def test_x86_converters_on_candidate_dense_buffers(emu, ora):
+    """Both x86 BCJ converters of lzb_post.cuh (per-lane segments under the lean form, the tile scan under the look-ahead
+    form) against the oracle on buffers that are mostly opcode candidates and fill bytes: every carried state, both
+    directions, sizes around the 16-byte tile, unaligned buffer starts (the emulation's arenas start at offset 5)."""
+    rng = np.random.default_rng(20260)
+    for it in range(1500):
+        n = int(rng.choice([5, 6, 9, 15, 16, 17, 20, 31, 32, 33, 47, 48, 49, 64, 100, 257, 1000]))
+        if it % 3 == 0:
+            d = rng.integers(0, 256, n, dtype=np.uint8)
+        elif it % 3 == 1:
+            d = rng.choice(np.array([0xE8, 0xE9, 0x00, 0xFF, 0x12, 0x80], dtype=np.uint8), n, p=[.25, .15, .25, .2, .1, .05])
+        else:
+            d = rng.choice(np.array([0xE8, 0x00, 0xFF], dtype=np.uint8), n)
+        ip, st, enc = int(rng.integers(0, 1 << 32)), int(rng.integers(0, 8)), int(rng.integers(0, 2))
+        w, g = ora.x86_convert(d, ip, st, enc), emu.x86_convert(d, ip, st, enc)
+        assert np.array_equal(w[0], g[0]) and w[1:] == g[1:], (n, ip, st, enc)
+
+
 @pytest.mark.needref
 def test_branch_converter_golden_equals_live_reference(ref):
     cs, blobs = cases.bra_golden()

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <new>
 #include <string>
 #include <thread>
 
@@ -30,6 +31,14 @@ void lzb_set_error(const char *fmt, ...)
 }
 
 extern "C" const char *Lzb_LastError(void) { return g_err; }
+
+/* No C++ exception leaves the C-ABI: an allocation that fails inside a batch entry point is SZ_ERROR_MEM for the caller. */
+template <class F> static SRes lzb_guarded(F &&body)
+{
+  try { return body(); }
+  catch (const std::bad_alloc &) { lzb_set_error("out of host memory"); return SZ_ERROR_MEM; }
+  catch (...) { lzb_set_error("unexpected internal error"); return SZ_ERROR_FAIL; }
+}
 
 bool lzb_cuda_ok(cudaError_t e, const char *what)
 {
@@ -435,7 +444,7 @@ SRes lzb_flow_then_checks(LzbContext *c, const Byte *packed, size_t packedBytes,
   return SZ_OK;
 }
 
-extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+static SRes Lzb_DecodeUnitsHost_body(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
                                     const LzbUnit *units, LzbResult *results, size_t n)
 {
   if (!c) { lzb_set_error("null context"); return SZ_ERROR_PARAM; }
@@ -553,6 +562,12 @@ extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t pa
 }
 
 /* ------------------------------------------------------------------ several GPUs of one box --- */
+extern "C" SRes Lzb_DecodeUnitsHost(LzbContext *c, const Byte *packed, size_t packedBytes, Byte *out, size_t outBytes,
+                                    const LzbUnit *units, LzbResult *results, size_t n)
+{
+  return lzb_guarded([&]() { return Lzb_DecodeUnitsHost_body(c, packed, packedBytes, out, outBytes, units, results, n); });
+}
+
 extern "C" void Lzb_ShardBounds(const LzbUnit *units, size_t n, size_t world, size_t *bounds)
 {
   if (world == 0) return;
@@ -571,7 +586,7 @@ extern "C" void Lzb_ShardBounds(const LzbUnit *units, size_t n, size_t world, si
   bounds[world] = n;
 }
 
-extern "C" SRes Lzb_DecodeUnitsHostMulti(LzbContext *const *ctxs, size_t nCtx, const Byte *packed, size_t packedBytes, Byte *out,
+static SRes Lzb_DecodeUnitsHostMulti_body(LzbContext *const *ctxs, size_t nCtx, const Byte *packed, size_t packedBytes, Byte *out,
                                          size_t outBytes, const LzbUnit *units, LzbResult *results, size_t n)
 {
   if (nCtx == 0 || !ctxs) { lzb_set_error("no context"); return SZ_ERROR_PARAM; }
@@ -581,9 +596,14 @@ extern "C" SRes Lzb_DecodeUnitsHostMulti(LzbContext *const *ctxs, size_t nCtx, c
   std::vector<SRes> verdict(nCtx, SZ_OK);
   std::vector<std::string> errors(nCtx);
   std::vector<std::thread> workers;
+  workers.reserve(nCtx);
+  bool spawned = true;
+  /* a range is failed until its worker says otherwise (a worker that never started leaves it that way) */
   for (size_t r = 0; r < nCtx; r++)
+    if (bounds[r] != bounds[r + 1]) { verdict[r] = SZ_ERROR_MEM; errors[r] = "the range's worker did not run (out of memory or threads)"; }
+  for (size_t r = 0; r < nCtx && spawned; r++)
   {
-    workers.emplace_back([&, r]()
+    auto work = [&, r]()
     {
       const size_t lo = bounds[r], hi = bounds[r + 1];
       if (lo == hi) return;
@@ -600,7 +620,10 @@ extern "C" SRes Lzb_DecodeUnitsHostMulti(LzbContext *const *ctxs, size_t nCtx, c
       verdict[r] = Lzb_DecodeUnitsHost(ctxs[r], packed + s_lo, (size_t)(s_hi - s_lo), out + d_lo, (size_t)(d_hi - d_lo),
                                        mine.data(), results + lo, hi - lo);
       if (verdict[r] != SZ_OK) errors[r] = Lzb_LastError();          /* (the error text is per thread) */
-    });
+    };
+    /* a range that cannot get its thread or its copy of the table fails alone; the started ones are always joined */
+    try { workers.emplace_back([&verdict, r, work]() { try { work(); } catch (...) { verdict[r] = SZ_ERROR_MEM; } }); }
+    catch (...) { verdict[r] = SZ_ERROR_MEM; spawned = false; }
   }
   for (std::thread &t : workers) t.join();
   SRes worst = SZ_OK;
@@ -724,6 +747,12 @@ SRes lzb_run_stages(LzbContext *c, const Byte *packed, size_t packedBytes, Byte 
 }
 
 /* ------------------------------------------------------------------ props ------------------- */
+extern "C" SRes Lzb_DecodeUnitsHostMulti(LzbContext *const *ctxs, size_t nCtx, const Byte *packed, size_t packedBytes, Byte *out,
+                                         size_t outBytes, const LzbUnit *units, LzbResult *results, size_t n)
+{
+  return lzb_guarded([&]() { return Lzb_DecodeUnitsHostMulti_body(ctxs, nCtx, packed, packedBytes, out, outBytes, units, results, n); });
+}
+
 extern "C" SRes LzmaProps_Decode(CLzmaProps *p, const Byte *data, unsigned size)
 {
   /* reference LzmaDec.c:898-922: dictionary clamped up to 4 KiB, d < 225 */
@@ -880,7 +909,7 @@ extern "C" int LzmaUncompress(unsigned char *dest, size_t *destLen, const unsign
   return LzmaDecode(dest, destLen, src, srcLen, props, (unsigned)propsSize, LZMA_FINISH_ANY, &status, nullptr);
 }
 
-extern "C" SRes LzmaUncompressBatch(LzbContext *c, size_t n, unsigned char *const *dest, size_t *destLen,
+static SRes LzmaUncompressBatch_body(LzbContext *c, size_t n, unsigned char *const *dest, size_t *destLen,
                                     const unsigned char *const *src, size_t *srcLen, const unsigned char *props,
                                     size_t propsStride, SRes *res)
 {
@@ -963,6 +992,13 @@ uint64_t lzb_crc64_shift(uint64_t reg, uint64_t n)
 
 UInt32 g_CrcTable[256 * 8];
 UInt64 g_Crc64Table[256];
+
+extern "C" SRes LzmaUncompressBatch(LzbContext *c, size_t n, unsigned char *const *dest, size_t *destLen,
+                                    const unsigned char *const *src, size_t *srcLen, const unsigned char *props,
+                                    size_t propsStride, SRes *res)
+{
+  return lzb_guarded([&]() { return LzmaUncompressBatch_body(c, n, dest, destLen, src, srcLen, props, propsStride, res); });
+}
 
 extern "C" void CrcGenerateTable(void)
 {
